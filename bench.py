@@ -1,0 +1,337 @@
+"""bench.py -- headline benchmark of the parllel batch post-processing path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1], "C1"): one STEP = one pass of the hot path over one synthetic
+[T=1024, B=4096] float32 trajectory batch PER GPU (weak scaling; B is sharded, no data-path
+collective): EstimateAdvantage (GAE, gamma=0.99, lambda=0.95) followed by NormalizeAdvantage
+(whose (count, mean, M2) statistics are all-gathered and merged across ranks when N > 1).
+`value`  = transitions/s, whole job, inputs resident in HBM, CUDA-event time, max over ranks.
+`e2e`    = the same metric through the public Transform.__call__ API with HOST (pinned numpy)
+           leaves: H2D of reward/value/done/bootstrap and D2H of advantage/return_ every step.
+`roofline` is for the dominant kernel (the GAE scan): 17 algorithmic bytes / transition.
+`cpu_baseline` / `--impl reference`: the reference algorithm (oracle port: C scans + numpy
+reductions, oracle/) on the box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+T_STEPS, B_ENVS = 1024, 4096          # C1, per GPU
+GAMMA, LAMBDA, P_DONE = 0.99, 0.95, 0.01
+GAE_BYTES_PER_TRANSITION = 17          # read reward 4 + value 4 + done 1, write advantage 4 + return_ 4
+L2_BYTES = 126 * 2**20
+METRIC = "transform_transitions_per_s"
+UNIT = "transitions/s"
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def synth_batch(seed: int, T: int = T_STEPS, B: int = B_ENVS):
+    rng = np.random.default_rng(seed)
+    return dict(
+        reward=rng.standard_normal((T, B), dtype=np.float32),
+        value=rng.standard_normal((T, B), dtype=np.float32),
+        done=rng.random((T, B), dtype=np.float32) < P_DONE,
+        bootstrap_value=rng.standard_normal((B,), dtype=np.float32),
+    )
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples SM clock + throttle reasons of one GPU while the timed region runs."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int, period_s: float = 0.05):
+        self.index, self.period = index, period_s
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            self._handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+        except Exception:
+            self._nvml = None
+
+    def _sample(self):
+        try:
+            if self._nvml is not None:
+                n = self._nvml
+                self.samples.append(n.nvmlDeviceGetClockInfo(self._handle, n.NVML_CLOCK_SM))
+                self.max_mhz = n.nvmlDeviceGetMaxClockInfo(self._handle, n.NVML_CLOCK_SM)
+                mask = n.nvmlDeviceGetCurrentClocksEventReasons(self._handle)
+                for name, bit in (("hw_slowdown", n.nvmlClocksEventReasonHwSlowdown),
+                                  ("hw_thermal_slowdown", n.nvmlClocksEventReasonHwThermalSlowdown),
+                                  ("sw_thermal_slowdown", n.nvmlClocksEventReasonSwThermalSlowdown),
+                                  ("sw_power_cap", n.nvmlClocksEventReasonSwPowerCap)):
+                    if mask & bit:
+                        self.reasons.add(name)
+            else:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                self.samples.append(int(parts[0]))
+                self.max_mhz = int(parts[1])
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[2:]):
+                    if val.lower().startswith("active"):
+                        self.reasons.add(name)
+        except Exception:
+            pass
+
+    def __enter__(self):
+        def loop():
+            while not self._stop.is_set():
+                self._sample()
+                self._stop.wait(self.period)
+        self._thread = threading.Thread(target=loop, daemon=True)
+        self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._sample()
+        self._stop.set()
+        self._thread.join(timeout=5)
+
+    def summary(self):
+        return {"sm_mhz": int(statistics.median(self.samples)) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ----------------------------------------------------------------------------- CPU arm
+def cpu_reference_arm(steps: int, warmup: int, budget_s: float, threads: int):
+    """The reference algorithm on host cores: oracle C scans (column blocks over a thread pool; the
+    numba original is single-threaded) + numpy float32 reductions, same step as the GPU arm."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from oracle import oracle as O
+
+    O.lib()
+    batch = synth_batch(1)
+    adv = np.empty_like(batch["value"])
+    ret = np.empty_like(batch["value"])
+    blocks = np.array_split(np.arange(B_ENVS), threads)
+    pool = ThreadPoolExecutor(threads)
+
+    def scan_block(cols):
+        lo, hi = int(cols[0]), int(cols[-1]) + 1
+        O.compute_gae_advantage(batch["reward"][:, lo:hi], batch["value"][:, lo:hi], batch["done"][:, lo:hi],
+                                batch["bootstrap_value"][lo:hi], GAMMA, LAMBDA, adv[:, lo:hi], ret[:, lo:hi])
+
+    def step():
+        list(pool.map(scan_block, blocks))
+        O.normalize_advantage(adv)
+
+    for _ in range(max(warmup, 1)):
+        step()
+    times = []
+    t_start = time.perf_counter()
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_start > budget_s and len(times) >= 3:
+            break
+    pool.shutdown()
+    per_step = sum(times) / len(times)
+    return {"value": T_STEPS * B_ENVS / per_step, "ms_per_step": per_step * 1e3, "steps": len(times)}
+
+
+# ----------------------------------------------------------------------------- main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer e2e loop (0 = min(steps, 40))")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    workload = (f"C1 per GPU: EstimateAdvantage(GAE gamma={GAMMA} lambda={LAMBDA}) + NormalizeAdvantage on synthetic "
+                f"[T={T_STEPS},B={B_ENVS}] float32, done p={P_DONE}")
+    config = {"workload": workload, "T": T_STEPS, "B_per_gpu": B_ENVS, "B_total": B_ENVS * max(world, 1),
+              "sharding": "env axis B split across ranks; stats (count,mean,M2) all-gathered when N>1",
+              "l2_policy": "inputs rotate over buffer sets totalling > 2x L2, so every step reads HBM"}
+    cores = os.cpu_count() or 1
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        threads = min(cores, 32)
+        res = cpu_reference_arm(args.steps, warmup, budget_s=60.0, threads=threads)
+        line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
+                "steps": res["steps"], "warmup": warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64 step / f32 store", "data": "synthetic",
+                "config": config,
+                "cpu_baseline": {"value": res["value"], "unit": UNIT, "cores": threads, "kind": "port",
+                                 "sample": f"{res['steps']} full C1 steps (oracle C scans over {threads} threads + numpy reductions)"},
+                "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from parllel_b200 import ArrayDict
+    from parllel_b200.transforms import EstimateAdvantage, NormalizeAdvantage
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    distributed = world > 1
+    if distributed:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    # buffer sets: enough that consecutive steps never hit L2
+    set_bytes = T_STEPS * B_ENVS * GAE_BYTES_PER_TRANSITION
+    n_sets = max(3, int(np.ceil(2.2 * L2_BYTES / set_bytes)))
+    sets = []
+    for i in range(n_sets):
+        b = synth_batch(1000 * rank + i + 1)
+        t = {k: torch.from_numpy(v).to(dev) for k, v in b.items()}
+        sets.append(ArrayDict({"reward": t["reward"], "done": t["done"], "agent_info": {"value": t["value"]},
+                               "bootstrap_value": t["bootstrap_value"],
+                               "advantage": torch.empty_like(t["value"]), "return_": torch.empty_like(t["value"])}))
+    ea = EstimateAdvantage(GAMMA, LAMBDA, algo="chunked")
+    na = NormalizeAdvantage(sets[0]) if not distributed else None
+    if distributed:
+        from parllel_b200.distributed import ShardedNormalizeAdvantage
+        na = ShardedNormalizeAdvantage(sets[0])
+
+    def step(i):
+        tree = sets[i % n_sets]
+        ea(tree)
+        na(tree)
+
+    for i in range(warmup):
+        step(i)
+    torch.cuda.synchronize()
+    if distributed:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+    stream = torch.cuda.current_stream(dev)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    with ClockSampler(local_rank) as clocks:
+        ev0.record(stream)
+        for i in range(args.steps):
+            tree = sets[i % n_sets]
+            k_ev[i][0].record(stream)
+            ea(tree)
+            k_ev[i][1].record(stream)
+            na(tree)
+        ev1.record(stream)
+        torch.cuda.synchronize()
+        if args.steps * 0.03 < 300:  # keep the GPU busy long enough for >= a few clock samples
+            t_end = time.perf_counter() + 0.4
+            j = 0
+            while time.perf_counter() < t_end:
+                step(j)
+                j += 1
+            torch.cuda.synchronize()
+    if distributed:
+        dist.barrier()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    gae_ms = [a.elapsed_time(b) for a, b in k_ev]
+    if distributed:
+        tmax = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(tmax.item())
+    transitions = T_STEPS * B_ENVS * world * args.steps
+    value = transitions / (elapsed_ms * 1e-3)
+
+    # ---- e2e: public API with HOST leaves (pinned), H2D + kernels + D2H per step --------------
+    from parllel_b200.host_pipeline import PinnedBatch
+    e2e_steps = args.e2e_steps or min(args.steps, 40)
+    host_sets = [PinnedBatch(synth_batch(7000 + 10 * rank + i)) for i in range(2)]
+    e2e_ea = EstimateAdvantage(GAMMA, LAMBDA, algo="chunked")
+    e2e_na = NormalizeAdvantage(host_sets[0].tree) if not distributed else na.__class__(host_sets[0].tree)
+    for i in range(3):
+        t = host_sets[i % 2].tree
+        e2e_na(e2e_ea(t))
+    torch.cuda.synchronize()
+    if distributed:
+        dist.barrier()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(e2e_steps):
+        t = host_sets[i % 2].tree
+        e2e_na(e2e_ea(t))
+    e1.record(stream)
+    torch.cuda.synchronize()
+    e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
+    if distributed:
+        tmax = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        e2e_ms = float(tmax.item())
+    e2e_value = T_STEPS * B_ENVS * world * e2e_steps / (e2e_ms * 1e-3)
+    h2d = T_STEPS * B_ENVS * 9 + B_ENVS * 4
+    d2h = T_STEPS * B_ENVS * 8 * 2  # advantage crosses twice on the unfused host path (GAE, then normalise)
+
+    if rank != 0:
+        if distributed:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peak()
+    gae_s = statistics.mean(gae_ms) * 1e-3
+    achieved = T_STEPS * B_ENVS * GAE_BYTES_PER_TRANSITION / gae_s / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
+        "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64 scan carries / f32 storage", "data": "synthetic", "config": config,
+        "clocks": clocks.summary(),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
+                "api": "EstimateAdvantage.__call__ + NormalizeAdvantage.__call__ on pinned numpy leaves"},
+        "gpu_launches": args.steps * 3,
+        "roofline": {"bound": "hbm", "kernel": "scan_chunked_kernel<GAE> (EstimateAdvantage)",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "peak_source": peak_src, "traffic": None,
+                     "algorithmic_bytes_per_launch": T_STEPS * B_ENVS * GAE_BYTES_PER_TRANSITION,
+                     "avg_launch_us": gae_s * 1e6,
+                     "frac_of_nominal_8TBs": achieved / 8000.0},
+    }
+    if not args.no_cpu_baseline:
+        res = cpu_reference_arm(steps=200, warmup=1, budget_s=12.0, threads=1)
+        line["cpu_baseline"] = {"value": res["value"], "unit": UNIT, "cores": 1, "kind": "port",
+                                "sample": f"{res['steps']} full C1 steps, single thread like the numba original "
+                                          f"(oracle C scans + numpy reductions); host has {cores} cores"}
+    print(json.dumps(line))
+    if distributed:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

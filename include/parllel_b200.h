@@ -1,0 +1,215 @@
+/*
+ * parllel_b200.h -- C ABI of libparllel_b200.so: the B200 (sm_100a) implementation of
+ * parllel's batch post-processing hot path (Transform pipeline + ReplayBuffer gather).
+ *
+ * This is the drop-in boundary.  Each entry point replaces one compiled/numpy
+ * routine of the reference (file:line relative to the upstream repository root is
+ * cited at every declaration); INTEGRATION.md shows the ctypes binding a parllel
+ * maintainer would add on the reference side.
+ *
+ * Conventions (all entry points):
+ *   - plain C types only; every data pointer is a DEVICE pointer unless it says HOST;
+ *   - time-major [T, B(, inner)] arrays, the column axis contiguous, one explicit row
+ *     stride per array in ELEMENTS (`ld_*`), exactly the views parllel's Array hands
+ *     to numba (parllel/arrays/array.py:420-431);
+ *   - float arrays are float32, masks are 1-byte bool (0 / non-zero), statistics and
+ *     scalar hyper-parameters are float64 -- the reference's dtypes;
+ *   - asynchronous and stream-ordered on `stream` (a cudaStream_t passed as void*);
+ *     no allocation, no host synchronisation, no host<->device copies inside;
+ *   - the caller owns all memory, including `workspace` (size from the matching
+ *     `*_workspace_bytes` query; must be zero-filled ONCE before its first use and is
+ *     left ready for reuse by every call; one workspace must not be shared by calls
+ *     that may run concurrently on different streams);
+ *   - returns 0 on success, a positive cudaError_t, or a negative PLB_ERR_* code;
+ *     `plb_last_error()` returns a thread-local description of the last failure.
+ */
+#ifndef PARLLEL_B200_H
+#define PARLLEL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define PLB_API __attribute__((visibility("default")))
+#else
+#define PLB_API
+#endif
+
+#define PLB_VERSION 100 /* 0.1.0 */
+
+#define PLB_OK 0
+#define PLB_ERR_INVALID_ARGUMENT (-1)
+#define PLB_ERR_UNSUPPORTED (-2)
+#define PLB_ERR_WORKSPACE (-3)
+
+/* scan algorithm selection */
+#define PLB_ALGO_AUTO 0
+#define PLB_ALGO_SERIAL 1  /* one thread per column, float64 step + float32 store: the
+                              reference's per-step rounding, bit-identical to oracle/plb_oracle.c */
+#define PLB_ALGO_CHUNKED 2 /* TMA-staged chunked affine scan (float64 carries); |err| <= ~3e-6 */
+
+/* flags for plb_update_from_moments_f64 */
+#define PLB_MOMENTS_F32_FLOW 1 /* batch mean/var rounded to float32 and batch_var*count evaluated
+                                  in float32, the numba typing of running_mean_std.py:52-53,27 */
+
+/* flags for the normalisation entry points */
+#define PLB_EPS_ON_VAR 0 /* x / sqrt(var + eps)   (norm_rewards.py:114, norm_obs.py:72-74) */
+#define PLB_EPS_ON_STD 1 /* x / (std + eps)       (norm_advantage.py:54)                   */
+
+typedef void *plb_stream_t; /* cudaStream_t */
+
+PLB_API int plb_version(void);
+PLB_API const char *plb_last_error(void);
+/* Number of SMs of the current device (grid sizing); <0 on error. */
+PLB_API int plb_sm_count(void);
+
+/* ------------------------------------------------------------------------------------
+ * EstimateAdvantage            parllel/transforms/advantage.py:36-57 (compute_gae_advantage)
+ *   adv[T-1] = r[T-1] + g*boot*nd[T-1] - v[T-1]
+ *   adv[t]   = r[t] + g*v[t+1]*nd[t] - v[t] + g*l*nd[t]*adv[t+1];   ret = adv + v (float32)
+ * `inner` > 1: value/bootstrap/advantage/return_ carry a trailing agent axis of that size
+ * while reward/done do not (parllel/transforms/multi_advantage.py:118-146 broadcast).
+ * ---------------------------------------------------------------------------------- */
+PLB_API int plb_compute_gae_advantage_f32(
+    const float *reward, int64_t ld_reward,
+    const float *value, int64_t ld_value,
+    const uint8_t *done, int64_t ld_done,
+    const float *bootstrap_value,
+    float *out_advantage, int64_t ld_advantage,
+    float *out_return, int64_t ld_return,
+    int64_t T, int64_t B, int64_t inner,
+    double discount, double gae_lambda,
+    int algo, plb_stream_t stream);
+
+/* parllel/transforms/advantage.py:11-33 (compute_discount_return), the lambda == 1 branch
+ *   ret[T-1] = r[T-1] + g*boot*nd[T-1];  ret[t] = r[t] + ret[t+1]*g*nd[t];  adv = ret - v */
+PLB_API int plb_compute_discount_return_f32(
+    const float *reward, int64_t ld_reward,
+    const float *value, int64_t ld_value,
+    const uint8_t *done, int64_t ld_done,
+    const float *bootstrap_value,
+    float *out_advantage, int64_t ld_advantage,
+    float *out_return, int64_t ld_return,
+    int64_t T, int64_t B, int64_t inner,
+    double discount,
+    int algo, plb_stream_t stream);
+
+/* parllel/transforms/norm_rewards.py:16-33 (compute_past_discount_return)
+ *   out[0] = r[0] + prev_return*g*~prev_done;  out[t] = r[t] + out[t-1]*g*~done[t-1]
+ * previous_return / previous_done are the [B] padding rows past_return[-1] / done[-1]
+ * (norm_rewards.py:92,95). */
+PLB_API int plb_compute_past_discount_return_f32(
+    const float *reward, int64_t ld_reward,
+    const uint8_t *done, int64_t ld_done,
+    const float *previous_return, const uint8_t *previous_done,
+    float *out_return, int64_t ld_out,
+    int64_t T, int64_t B,
+    double discount,
+    int algo, plb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * RunningMeanStd               parllel/transforms/running_mean_std.py:49-57
+ * Batch moments (np.mean / np.var, :52-53) as a Welford/Chan parallel reduction.
+ * Moments are always the triple (count, mean, M2 = sum (x-mean)^2) in float64.
+ * ---------------------------------------------------------------------------------- */
+/* Moments of ALL elements of a [rows, cols] region (or of those with valid != 0;
+ * `valid` may be NULL).  Writes moments_out[3] = (count, mean, M2). */
+PLB_API size_t plb_batch_moments_workspace_bytes(void);
+PLB_API int plb_batch_moments_f32(
+    const float *x, int64_t ld_x, int64_t rows, int64_t cols,
+    const uint8_t *valid, int64_t ld_valid,
+    double *moments_out,
+    void *workspace, size_t workspace_bytes, plb_stream_t stream);
+
+/* Per-column moments of a [rows, cols] region over the rows with row_valid != 0
+ * (row_valid may be NULL).  Writes count_out[1], mean_out[cols], m2_out[cols]. */
+PLB_API size_t plb_column_moments_workspace_bytes(int64_t rows, int64_t cols);
+PLB_API int plb_column_moments_f32(
+    const float *x, int64_t ld_x, int64_t rows, int64_t cols,
+    const uint8_t *row_valid,
+    double *count_out, double *mean_out, double *m2_out,
+    void *workspace, size_t workspace_bytes, plb_stream_t stream);
+
+/* Multi-GPU exchange step: merge `n_parts` per-rank moments (all-gathered by the host through
+ * NCCL) in rank order, so every rank derives bit-identical statistics.  This is the exact
+ * parallel merge that replaces the reference's only collective, the mean-of-variances
+ * all_reduce in parllel/torch/models.py:212-218.
+ *   layout 0: parts[n_parts][n_cols][3] (count, mean, M2) triples -> out[n_cols][3]
+ *   layout 1: parts[n_parts][1 + 2*n_cols] (count, mean[], M2[])  -> out[1 + 2*n_cols] */
+PLB_API int plb_merge_moments_f64(
+    const double *parts, int32_t n_parts, int64_t n_cols, int layout, double *out,
+    plb_stream_t stream);
+
+/* parllel/transforms/running_mean_std.py:7-32 (update_from_moments): float64 Chan merge
+ * of device-resident batch moments into the device-resident running state
+ * (mean[n], var[n], count[1]).  batch_var = batch_m2 / batch_count. */
+PLB_API int plb_update_from_moments_f64(
+    const double *batch_count, const double *batch_mean, const double *batch_m2,
+    double *mean, double *var, double *count, int64_t n,
+    int flags, plb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * Elementwise passes
+ * ---------------------------------------------------------------------------------- */
+/* NormalizeRewards tail + ClipRewards fused:  x = clip( float32( x / sqrt(var + eps) ) )
+ *   parllel/transforms/norm_rewards.py:114 and parllel/transforms/clip_rewards.py:36.
+ * `var` is a DEVICE pointer to the running float64 variance, or NULL for "no scaling";
+ * clip bounds are NaN for "no bound".  In place over a [rows, cols] region. */
+PLB_API int plb_scale_clip_f32(
+    float *x, int64_t ld_x, int64_t rows, int64_t cols,
+    const double *var, double eps, double clip_lo, double clip_hi,
+    plb_stream_t stream);
+
+/* NormalizeAdvantage tail      parllel/transforms/norm_advantage.py:51-54
+ *   adv = (adv - float32(mean)) / (float32(std) + float32(eps)),  all in float32,
+ * with per-`inner` statistics moments[inner][3] = (count, mean, M2) on the device. */
+PLB_API int plb_normalize_advantage_f32(
+    float *advantage, int64_t ld, int64_t rows, int64_t cols, int64_t inner,
+    const double *moments, double eps, plb_stream_t stream);
+
+/* NormalizeObservations tail   parllel/transforms/norm_obs.py:72-74
+ *   obs[r, f] = float32( (obs[r, f] - mean[f]) / sqrt(var[f] + eps) )   (float64 arithmetic) */
+PLB_API int plb_normalize_columns_f32(
+    float *x, int64_t ld_x, int64_t rows, int64_t cols,
+    const double *mean, const double *var, double eps, plb_stream_t stream);
+
+/* NormalizeObservations.__call__ for one step   parllel/transforms/norm_obs.py:57-76
+ * update running stats from obs[row_valid] FIRST, then normalise all rows with the
+ * updated stats.  Single entry; chooses the on-chip single-pass kernel when a
+ * [rows x column-tile] slab fits in shared memory, else a 3-kernel sequence. */
+PLB_API size_t plb_normalize_observations_workspace_bytes(int64_t rows, int64_t cols);
+PLB_API int plb_normalize_observations_step_f32(
+    float *obs, int64_t ld_obs, int64_t rows, int64_t cols,
+    const uint8_t *row_valid,
+    double *mean, double *var, double *count, double eps, int flags,
+    void *workspace, size_t workspace_bytes, plb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * ReplayBuffer.sample_batch gather      parllel/replays/replay.py:72  (tree[T_idxs, B_idxs])
+ * One launch gathers every leaf of the ring tree: dst[i, :] = src[t_idx[i], b_idx[i], :].
+ * ---------------------------------------------------------------------------------- */
+typedef struct {
+    const void *src;        /* leaf base: element [0, 0, ...] of the visible ring window   */
+    void *dst;              /* [n, row_bytes] dense output                                 */
+    int64_t row_bytes;      /* bytes of one (t, b) entry (prod(feature_shape) * itemsize)  */
+    int64_t stride_t_bytes; /* bytes between consecutive t                                 */
+    int64_t stride_b_bytes; /* bytes between consecutive b                                 */
+} plb_gather_leaf;
+
+#define PLB_GATHER_MAX_LEAVES 16
+
+/* `leaves` is a HOST array (copied into the kernel's parameter space); t_idx / b_idx are
+ * DEVICE int64[n]. */
+PLB_API int plb_gather_tree(
+    const plb_gather_leaf *leaves, int32_t n_leaves,
+    const int64_t *t_idx, const int64_t *b_idx, int64_t n,
+    plb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PARLLEL_B200_H */

@@ -1,0 +1,112 @@
+"""ctypes binding of ``libparllel_b200.so`` (the C ABI in ``include/parllel_b200.h``).
+
+There is no CPU fallback: if the CUDA library is missing this module raises at
+first use, loudly, instead of routing the hot path anywhere else.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_double, c_int, c_int32, c_int64, c_size_t, c_void_p
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG_DIR, "libparllel_b200.so")
+
+ALGO_AUTO, ALGO_SERIAL, ALGO_CHUNKED = 0, 1, 2
+MOMENTS_F32_FLOW = 1
+GATHER_MAX_LEAVES = 16
+NAN = float("nan")
+
+
+class PlbError(RuntimeError):
+    """A libparllel_b200 entry point returned non-zero."""
+
+
+class GatherLeaf(ctypes.Structure):
+    _fields_ = [("src", c_void_p), ("dst", c_void_p), ("row_bytes", c_int64),
+                ("stride_t_bytes", c_int64), ("stride_b_bytes", c_int64)]
+
+
+_SIGNATURES = {
+    "plb_version": ([], c_int),
+    "plb_last_error": ([], ctypes.c_char_p),
+    "plb_sm_count": ([], c_int),
+    "plb_compute_gae_advantage_f32": (
+        [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64,
+         c_int64, c_int64, c_int64, c_double, c_double, c_int, c_void_p], c_int),
+    "plb_compute_discount_return_f32": (
+        [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64,
+         c_int64, c_int64, c_int64, c_double, c_int, c_void_p], c_int),
+    "plb_compute_past_discount_return_f32": (
+        [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64,
+         c_double, c_int, c_void_p], c_int),
+    "plb_batch_moments_workspace_bytes": ([], c_size_t),
+    "plb_batch_moments_f32": (
+        [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_size_t, c_void_p], c_int),
+    "plb_column_moments_workspace_bytes": ([c_int64, c_int64], c_size_t),
+    "plb_column_moments_f32": (
+        [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+         c_void_p], c_int),
+    "plb_merge_moments_f64": ([c_void_p, c_int32, c_int64, c_int, c_void_p, c_void_p], c_int),
+    "plb_update_from_moments_f64": (
+        [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p], c_int),
+    "plb_scale_clip_f32": (
+        [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_double, c_double, c_double, c_void_p], c_int),
+    "plb_normalize_advantage_f32": (
+        [c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_double, c_void_p], c_int),
+    "plb_normalize_columns_f32": (
+        [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_double, c_void_p], c_int),
+    "plb_normalize_observations_workspace_bytes": ([c_int64, c_int64], c_size_t),
+    "plb_normalize_observations_step_f32": (
+        [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_int,
+         c_void_p, c_size_t, c_void_p], c_int),
+    "plb_gather_tree": (
+        [ctypes.POINTER(GatherLeaf), c_int32, c_void_p, c_void_p, c_int64, c_void_p], c_int),
+}
+
+# entry points added after the first release are bound when present (see include/parllel_b200.h)
+_OPTIONAL = {
+    "plb_batch_pipeline_workspace_bytes": ([], c_size_t),
+    "plb_batch_pipeline_f32": ([c_void_p, c_void_p], c_int),
+    "plb_replay_sample_indices": None,
+}
+
+_lib = None
+
+
+def library_path() -> str:
+    return LIB_PATH
+
+
+def load() -> ctypes.CDLL:
+    """Load the CUDA library; raise if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise PlbError(
+            f"{LIB_PATH} is missing: build it with `python -m parllel_b200.build` "
+            "(nvcc, sm_100a).  parllel_b200 has no CPU fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (argtypes, restype) in _SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here = header/library mismatch: fail loudly
+        fn.argtypes = argtypes
+        fn.restype = restype
+    for name, sig in _OPTIONAL.items():
+        if sig is not None and hasattr(lib, name):
+            fn = getattr(lib, name)
+            fn.argtypes, fn.restype = sig
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().plb_last_error()
+        msg = msg.decode("utf-8", "replace") if msg else ""
+        kind = "CUDA error" if rc > 0 else "library error"
+        raise PlbError(f"{what or 'libparllel_b200'}: {kind} {rc}: {msg}")
+
+
+def exported_symbols() -> list[str]:
+    return sorted(_SIGNATURES)

@@ -1,0 +1,48 @@
+// plb_api.cu -- library-level entry points: version, error string, device query.
+#include <stdarg.h>
+
+#include "plb_common.cuh"
+
+namespace plb {
+
+static thread_local char g_last_error[512] = "";
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap);
+    va_end(ap);
+}
+
+int sm_count()
+{
+    static thread_local int cached_dev = -1;
+    static thread_local int cached_sms = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+    if (dev != cached_dev) {
+        int sms = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+        cached_dev = dev;
+        cached_sms = sms;
+    }
+    return cached_sms;
+}
+
+}  // namespace plb
+
+extern "C" {
+
+int plb_version(void) { return PLB_VERSION; }
+
+const char *plb_last_error(void) { return plb::g_last_error; }
+
+int plb_sm_count(void)
+{
+    const int n = plb::sm_count();
+    if (n < 0) plb::set_error("no CUDA device available");
+    return n;
+}
+
+}  // extern "C"

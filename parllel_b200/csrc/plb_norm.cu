@@ -1,0 +1,299 @@
+// plb_norm.cu -- elementwise normalisation / clipping passes and the NormalizeObservations step.
+//   reward scale + clip      parllel/transforms/norm_rewards.py:114, clip_rewards.py:36
+//   advantage normalisation  parllel/transforms/norm_advantage.py:51-54
+//   observation normalise    parllel/transforms/norm_obs.py:57-76
+#include <math.h>
+
+#include "plb_common.cuh"
+#include "plb_scan_shared.cuh"
+
+namespace plb {
+
+// Generic 2-D elementwise driver: F(value, column) over a [rows, cols] region in place,
+// 128-bit accesses when the region allows it.
+template <bool VEC4, class F>
+__global__ void __launch_bounds__(256)
+elementwise_kernel(float *__restrict__ x, int64_t ld_x, int64_t rows, int64_t cols, F f)
+{
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+    if (VEC4) {
+        const int64_t vpr = cols >> 2;
+        const int64_t total = rows * vpr;
+        constexpr int U = 4;
+        for (int64_t base = tid; base < total; base += nthreads * U) {
+            float4 v[U];
+            int64_t off[U], col[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int64_t i = base + (int64_t)u * nthreads;
+                if (i < total) {
+                    const int64_t r = (rows == 1) ? 0 : i / vpr;
+                    col[u] = (i - r * vpr) << 2;
+                    off[u] = r * ld_x + col[u];
+                    v[u] = *reinterpret_cast<const float4 *>(x + off[u]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int64_t i = base + (int64_t)u * nthreads;
+                if (i < total) {
+                    float4 o;
+                    o.x = f(v[u].x, col[u]);
+                    o.y = f(v[u].y, col[u] + 1);
+                    o.z = f(v[u].z, col[u] + 2);
+                    o.w = f(v[u].w, col[u] + 3);
+                    *reinterpret_cast<float4 *>(x + off[u]) = o;
+                }
+            }
+        }
+    } else {
+        const int64_t total = rows * cols;
+        for (int64_t i = tid; i < total; i += nthreads) {
+            const int64_t r = (rows == 1) ? 0 : i / cols;
+            const int64_t c = i - r * cols;
+            x[r * ld_x + c] = f(x[r * ld_x + c], c);
+        }
+    }
+}
+
+template <class F>
+static int launch_elementwise(float *x, int64_t ld_x, int64_t rows, int64_t cols, bool col_dependent, F f,
+                              cudaStream_t stream)
+{
+    if (rows * cols == 0) return PLB_OK;
+    if (ld_x == cols && !col_dependent) {
+        cols = rows * cols;
+        rows = 1;
+        ld_x = cols;
+    }
+    const bool vec = (cols % 4 == 0) && (ld_x % 4 == 0) && aligned(x, 16);
+    const int64_t total = rows * cols;
+    const int sms = sm_count();
+    PLB_REQUIRE(sms > 0, PLB_ERR_UNSUPPORTED, "no CUDA device");
+    int64_t blocks = ceil_div(vec ? total / 4 : total, 256 * 4);
+    if (blocks < 1) blocks = 1;
+    if (blocks > (int64_t)sms * 16) blocks = (int64_t)sms * 16;
+    if (vec) elementwise_kernel<true, F><<<(unsigned)blocks, 256, 0, stream>>>(x, ld_x, rows, cols, f);
+    else elementwise_kernel<false, F><<<(unsigned)blocks, 256, 0, stream>>>(x, ld_x, rows, cols, f);
+    PLB_LAUNCH_CHECK();
+    return PLB_OK;
+}
+
+// reward = clip( float32( float64(reward) / sqrt(var + eps) ) )
+struct ScaleClipOp {
+    const double *var;
+    double eps;
+    float lo, hi;
+    __device__ __forceinline__ float operator()(float x, int64_t) const
+    {
+        if (var != nullptr) {
+            // one float64 division per element, like the reference (norm_rewards.py:114)
+            x = __double2float_rn(__ddiv_rn((double)x, sqrt(__dadd_rn(*var, eps))));
+        }
+        return fminf(fmaxf(x, lo), hi);
+    }
+};
+
+// advantage = (adv - mean32) / (std32 + eps32), float32 arithmetic (norm_advantage.py:51-54)
+struct NormAdvOp {
+    const double *moments;  // [inner][3]
+    int64_t inner;
+    float eps;
+    __device__ __forceinline__ float operator()(float x, int64_t col) const
+    {
+        const double *m = moments + 3 * (inner == 1 ? 0 : col % inner);
+        const float mean = __double2float_rn(m[1]);
+        const float stdv = __double2float_rn(sqrt(m[2] / m[0]));
+        return __fdiv_rn(__fsub_rn(x, mean), __fadd_rn(stdv, eps));
+    }
+};
+
+// obs = float32( (float64(obs) - mean[f]) / sqrt(var[f] + eps) )   (norm_obs.py:72-74)
+struct NormColsOp {
+    const double *mean, *var;
+    double eps;
+    __device__ __forceinline__ float operator()(float x, int64_t col) const
+    {
+        return __double2float_rn(__ddiv_rn(__dsub_rn((double)x, mean[col]), sqrt(__dadd_rn(var[col], eps))));
+    }
+};
+
+// column-tiled normalisation with the per-column (mean, 1/denominator) hoisted out of the row loop
+template <int VEC>
+__global__ void __launch_bounds__(128)
+normalize_columns_kernel(float *__restrict__ x, int64_t ld_x, int64_t rows, int64_t cols,
+                         const double *__restrict__ mean, const double *__restrict__ var, double eps,
+                         int64_t rows_per_split)
+{
+    const int64_t c0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+    if (c0 >= cols) return;
+    double mu[VEC], den[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+        mu[k] = mean[c0 + k];
+        den[k] = sqrt(__dadd_rn(var[c0 + k], eps));
+    }
+    const int64_t r_lo = (int64_t)blockIdx.y * rows_per_split;
+    const int64_t r_hi = (r_lo + rows_per_split < rows) ? r_lo + rows_per_split : rows;
+    constexpr int U = 4;
+    for (int64_t r = r_lo; r < r_hi; r += U) {
+        float v[U][VEC];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (r + u < r_hi) {
+                if (VEC == 4) {
+                    const float4 q = *reinterpret_cast<const float4 *>(x + (r + u) * ld_x + c0);
+                    v[u][0] = q.x; v[u][1 % VEC] = q.y; v[u][2 % VEC] = q.z; v[u][3 % VEC] = q.w;
+                } else {
+                    v[u][0] = x[(r + u) * ld_x + c0];
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (r + u < r_hi) {
+#pragma unroll
+                for (int k = 0; k < VEC; ++k)
+                    v[u][k] = __double2float_rn(__ddiv_rn(__dsub_rn((double)v[u][k], mu[k]), den[k]));
+                if (VEC == 4) {
+                    float4 q;
+                    q.x = v[u][0]; q.y = v[u][1 % VEC]; q.z = v[u][2 % VEC]; q.w = v[u][3 % VEC];
+                    *reinterpret_cast<float4 *>(x + (r + u) * ld_x + c0) = q;
+                } else {
+                    x[(r + u) * ld_x + c0] = v[u][0];
+                }
+            }
+        }
+    }
+}
+
+int normalize_columns(float *x, int64_t ld_x, int64_t rows, int64_t cols, const double *mean, const double *var,
+                      double eps, cudaStream_t stream)
+{
+    PLB_REQUIRE(rows >= 0 && cols >= 0, PLB_ERR_INVALID_ARGUMENT, "negative extent");
+    if (rows * cols == 0) return PLB_OK;
+    PLB_REQUIRE(x && mean && var, PLB_ERR_INVALID_ARGUMENT, "null pointer");
+    PLB_REQUIRE(ld_x >= cols, PLB_ERR_INVALID_ARGUMENT, "row stride smaller than row length");
+    const int splits = column_moments_splits(rows, cols);
+    const int64_t rows_per_split = ceil_div(rows, splits);
+    const bool vec = (cols % 4 == 0) && (ld_x % 4 == 0) && aligned(x, 16);
+    if (vec) {
+        dim3 grid((unsigned)ceil_div(cols / 4, 128), (unsigned)splits);
+        normalize_columns_kernel<4><<<grid, 128, 0, stream>>>(x, ld_x, rows, cols, mean, var, eps, rows_per_split);
+    } else {
+        dim3 grid((unsigned)ceil_div(cols, 128), (unsigned)splits);
+        normalize_columns_kernel<1><<<grid, 128, 0, stream>>>(x, ld_x, rows, cols, mean, var, eps, rows_per_split);
+    }
+    PLB_LAUNCH_CHECK();
+    return PLB_OK;
+}
+
+// finalize of the observation step: merge row splits, fold into the running state
+// (update_from_moments), leaving mean/var updated for the normalise pass.  `count` is
+// read by every CTA and written by nobody here; a follow-up single-thread kernel bumps it.
+__global__ void __launch_bounds__(256)
+obs_finalize_update_kernel(const Moments *__restrict__ partials, int64_t cols, int n_splits,
+                           double *mean, double *var, const double *count, double *batch_count_out, int flags)
+{
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    Moments acc = partials[c];
+    for (int s = 1; s < n_splits; ++s) acc = merge(acc, partials[(int64_t)s * cols + c]);
+    const double cnt = count[0];
+    // running_mean_std.py:23-30 with batch_var = M2 / n
+    double batch_mean = acc.mean;
+    double batch_var = acc.m2 / acc.n;
+    double m_b;
+    if (flags & PLB_MOMENTS_F32_FLOW) {
+        batch_mean = (double)__double2float_rn(batch_mean);
+        const float bv32 = __double2float_rn(batch_var);
+        m_b = (double)__fmul_rn(bv32, __double2float_rn(acc.n));
+    } else {
+        m_b = __dmul_rn(batch_var, acc.n);
+    }
+    const double m = mean[c], v = var[c];
+    const double delta = __dsub_rn(batch_mean, m);
+    const double total = __dadd_rn(acc.n, cnt);
+    mean[c] = __dadd_rn(m, __ddiv_rn(__dmul_rn(delta, acc.n), total));
+    const double cross = __ddiv_rn(__dmul_rn(__dmul_rn(__dmul_rn(delta, delta), cnt), acc.n), total);
+    var[c] = __ddiv_rn(__dadd_rn(__dadd_rn(__dmul_rn(v, cnt), m_b), cross), total);
+    if (c == 0) batch_count_out[0] = acc.n;
+}
+
+__global__ void bump_count_kernel(double *count, const double *batch_count) { count[0] = batch_count[0] + count[0]; }
+
+}  // namespace plb
+
+extern "C" {
+
+int plb_scale_clip_f32(float *x, int64_t ld_x, int64_t rows, int64_t cols, const double *var, double eps,
+                       double clip_lo, double clip_hi, plb_stream_t stream)
+{
+    using namespace plb;
+    PLB_REQUIRE(rows >= 0 && cols >= 0, PLB_ERR_INVALID_ARGUMENT, "negative extent");
+    if (rows * cols == 0) return PLB_OK;
+    PLB_REQUIRE(x != nullptr && ld_x >= cols, PLB_ERR_INVALID_ARGUMENT, "bad array");
+    ScaleClipOp op;
+    op.var = var;
+    op.eps = eps;
+    op.lo = (clip_lo != clip_lo) ? -INFINITY : (float)clip_lo;
+    op.hi = (clip_hi != clip_hi) ? INFINITY : (float)clip_hi;
+    return launch_elementwise(x, ld_x, rows, cols, false, op, (cudaStream_t)stream);
+}
+
+int plb_normalize_advantage_f32(float *advantage, int64_t ld, int64_t rows, int64_t cols, int64_t inner,
+                                const double *moments, double eps, plb_stream_t stream)
+{
+    using namespace plb;
+    PLB_REQUIRE(rows >= 0 && cols >= 0 && inner >= 1, PLB_ERR_INVALID_ARGUMENT, "bad extent");
+    if (rows * cols == 0) return PLB_OK;
+    PLB_REQUIRE(advantage && moments && ld >= cols && cols % inner == 0, PLB_ERR_INVALID_ARGUMENT, "bad array");
+    NormAdvOp op;
+    op.moments = moments;
+    op.inner = inner;
+    op.eps = (float)eps;
+    return launch_elementwise(advantage, ld, rows, cols, inner != 1, op, (cudaStream_t)stream);
+}
+
+int plb_normalize_columns_f32(float *x, int64_t ld_x, int64_t rows, int64_t cols, const double *mean,
+                              const double *var, double eps, plb_stream_t stream)
+{
+    return plb::normalize_columns(x, ld_x, rows, cols, mean, var, eps, (cudaStream_t)stream);
+}
+
+size_t plb_normalize_observations_workspace_bytes(int64_t rows, int64_t cols)
+{
+    if (rows < 0 || cols <= 0) return 64;
+    return 64 + sizeof(plb::Moments) * (size_t)plb::column_moments_splits(rows, cols) * (size_t)cols;
+}
+
+int plb_normalize_observations_step_f32(float *obs, int64_t ld_obs, int64_t rows, int64_t cols,
+                                        const uint8_t *row_valid, double *mean, double *var, double *count,
+                                        double eps, int flags, void *workspace, size_t workspace_bytes,
+                                        plb_stream_t stream_)
+{
+    using namespace plb;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    PLB_REQUIRE(rows >= 0 && cols >= 0, PLB_ERR_INVALID_ARGUMENT, "negative extent");
+    if (cols == 0) return PLB_OK;
+    PLB_REQUIRE(obs && mean && var && count, PLB_ERR_INVALID_ARGUMENT, "null pointer");
+    PLB_REQUIRE(ld_obs >= cols, PLB_ERR_INVALID_ARGUMENT, "row stride smaller than row length");
+    const size_t need = plb_normalize_observations_workspace_bytes(rows, cols);
+    PLB_REQUIRE(workspace != nullptr && workspace_bytes >= need, PLB_ERR_WORKSPACE,
+                "observation step needs %zu workspace bytes, got %zu", need, workspace_bytes);
+    double *batch_count = reinterpret_cast<double *>(workspace);
+    Moments *partials = reinterpret_cast<Moments *>(reinterpret_cast<unsigned char *>(workspace) + 64);
+
+    const int splits = column_moments_splits(rows, cols);
+    int rc = column_moments_partial(obs, ld_obs, rows, cols, row_valid, partials, splits, stream);
+    if (rc) return rc;
+    obs_finalize_update_kernel<<<(unsigned)ceil_div(cols, 256), 256, 0, stream>>>(partials, cols, splits, mean, var,
+                                                                                   count, batch_count, flags);
+    PLB_LAUNCH_CHECK();
+    bump_count_kernel<<<1, 1, 0, stream>>>(count, batch_count);
+    PLB_LAUNCH_CHECK();
+    return normalize_columns(obs, ld_obs, rows, cols, mean, var, eps, stream);
+}
+
+}  // extern "C"

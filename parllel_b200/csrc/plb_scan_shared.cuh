@@ -1,0 +1,206 @@
+// plb_scan_shared.cuh -- PTX wrappers (mbarrier, TMA) and the cross-CTA moments tail
+// shared by the scan, statistics and observation kernels.
+#pragma once
+
+#include <cuda.h>
+
+#include "plb_common.cuh"
+
+namespace plb {
+
+// ---------------------------------------------------------------------------------
+// Workspace layout for a grid-wide (count, mean, M2) reduction:
+//   [0, 64)            ticket counter (uint32) -- zero before first use, reset by the kernel
+//   [64, 64 + 24*MAX)  per-CTA partial moments
+// ---------------------------------------------------------------------------------
+constexpr int MOMENTS_MAX_PARTIALS = 4096;
+constexpr size_t MOMENTS_WS_BYTES = 64 + sizeof(Moments) * MOMENTS_MAX_PARTIALS;
+
+struct MomentsTail {
+    double *moments_out;  // [3] = (count, mean, M2); nullptr disables the tail
+    Moments *partials;
+    unsigned *ticket;
+};
+
+static inline MomentsTail make_tail(double *moments_out, void *workspace)
+{
+    MomentsTail t;
+    t.moments_out = moments_out;
+    t.ticket = reinterpret_cast<unsigned *>(workspace);
+    t.partials = reinterpret_cast<Moments *>(reinterpret_cast<unsigned char *>(workspace) + 64);
+    return t;
+}
+
+// Optional work fused into the chunked scans (host-side description).
+struct ScanFusion {
+    int has_pre;               // apply reward scale/clip on the load path
+    const double *reward_var;  // device running variance (float64) or nullptr
+    double reward_eps;
+    double clip_lo, clip_hi;   // NaN = no bound
+    float *reward_out;         // write the transformed reward back (may alias the input)
+    int64_t ld_reward_out;
+    const uint8_t *valid;      // mask for the fused moments (nullptr = all)
+    int64_t ld_valid;
+    MomentsTail tail;          // fused moments of advantage / past_return
+};
+
+int scan_reverse(int mode, const float *reward, int64_t ld_r, const float *value, int64_t ld_v,
+                 const uint8_t *done, int64_t ld_d, const float *boot,
+                 float *adv, int64_t ld_a, float *ret, int64_t ld_t,
+                 int64_t T, int64_t B, int64_t inner, double gamma, double lambda, int algo,
+                 const ScanFusion *fusion, cudaStream_t stream);
+int scan_forward(const float *reward, int64_t ld_r, const uint8_t *done, int64_t ld_d,
+                 const float *prev_ret, const uint8_t *prev_done, float *out, int64_t ld_o,
+                 int64_t T, int64_t B, double gamma, int algo, const ScanFusion *fusion, cudaStream_t stream);
+int column_moments_splits(int64_t rows, int64_t cols);
+int column_moments_partial(const float *x, int64_t ld_x, int64_t rows, int64_t cols, const uint8_t *row_valid,
+                           Moments *partials, int splits, cudaStream_t stream);
+int column_moments(const float *x, int64_t ld_x, int64_t rows, int64_t cols, const uint8_t *row_valid,
+                   double *count_out, double *mean_out, double *m2_out,
+                   void *workspace, size_t workspace_bytes, cudaStream_t stream);
+int make_tensor_map_2d(CUtensorMap *tm, const void *base, int elem_bytes, int64_t rows, int64_t cols,
+                       int64_t ld_elems, int box_rows, int box_cols);
+
+#ifdef __CUDACC__
+// ---------------------------------------------------------------------------------
+// mbarrier + TMA (inline PTX; SASS: SYNCS.*, UTMALDG / UBLKCP)
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void fence_mbar_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void fence_proxy_async_smem()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity)
+{
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0;
+    unsigned spins = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (done) break;
+        if (++spins > (1u << 24)) __trap();  // a lost TMA would otherwise hang the GPU
+    }
+}
+
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *tm)
+{
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
+}
+
+// 2-D tiled load: box at (c0 = column, c1 = row) -> shared, completes on `bar`.
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *tm, int c0, int c1,
+                                            unsigned long long *bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+
+// 2-D tiled store shared -> global (bulk async group)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *tm, const void *src, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read()
+{
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void tma_store_wait()
+{
+    asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// 1-D bulk copies (no tensor map): global -> shared on an mbarrier, shared -> global in a bulk group
+__device__ __forceinline__ void bulk_load_1d(void *dst, const void *src, uint32_t bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ void bulk_store_1d(void *dst, const void *src, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 ::"l"(reinterpret_cast<uint64_t>(dst)), "r"(smem_u32(src)), "r"(bytes)
+                 : "memory");
+}
+
+// ---------------------------------------------------------------------------------
+// Grid-wide moments tail: every CTA contributes one partial; the last CTA to arrive
+// merges all partials in index order (deterministic) and writes (count, mean, M2).
+// Must be called by ALL threads of EVERY CTA of the grid.  `scratch` >= 32 Moments.
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ void moments_tail(Moments mine, const MomentsTail &tail, Moments *scratch)
+{
+    __shared__ bool is_last;
+    __syncthreads();  // scratch may have been used before
+    Moments m = block_merge(mine, scratch);
+    if (threadIdx.x == 0) {
+        tail.partials[blockIdx.x] = m;
+        __threadfence();
+        const unsigned t = atomicAdd(tail.ticket, 1u);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    Moments acc;
+    acc.n = 0.0; acc.mean = 0.0; acc.m2 = 0.0;
+    // contiguous slices per thread keep the merge order = CTA index order
+    const unsigned n = gridDim.x;
+    const unsigned per = (n + blockDim.x - 1) / blockDim.x;
+    const unsigned lo = threadIdx.x * per;
+    for (unsigned i = lo; i < lo + per && i < n; ++i) {
+        const volatile Moments *vp = tail.partials + i;
+        Moments q;
+        q.n = vp->n; q.mean = vp->mean; q.m2 = vp->m2;
+        acc = merge(acc, q);
+    }
+    __syncthreads();
+    acc = block_merge(acc, scratch);
+    if (threadIdx.x == 0) {
+        tail.moments_out[0] = acc.n;
+        tail.moments_out[1] = acc.mean;
+        tail.moments_out[2] = acc.m2;
+        *tail.ticket = 0u;  // ready for the next launch
+    }
+}
+#endif  // __CUDACC__
+
+}  // namespace plb

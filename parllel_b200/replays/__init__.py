@@ -1,0 +1,4 @@
+"""B200-native drop-ins for parllel's replay containers (parllel/replays/__init__.py)."""
+from .replay import ReplayBuffer
+
+__all__ = ["ReplayBuffer"]

@@ -1,0 +1,195 @@
+"""GPU parity: EstimateAdvantage / past-return scans vs the golden reference outputs and the oracle.
+
+Bars (BASELINE.json north_star): GAE / returns within 1e-5 relative (floor = rms, tests/util.py);
+the SERIAL algorithm reproduces the reference's per-step float32 rounding and must be
+BIT-IDENTICAL to the strict-IEEE oracle (oracle/plb_oracle.c)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as O
+from tests.util import assert_within_tolerance, make_batch
+
+pytestmark = pytest.mark.gpu
+
+
+def _device_tree(batch, dev="cuda"):
+    from parllel_b200 import ArrayDict
+    t = {k: torch.from_numpy(v).to(dev) for k, v in batch.items()}
+    return ArrayDict({
+        "reward": t["reward"], "done": t["done"], "agent_info": {"value": t["value"]},
+        "bootstrap_value": t["bootstrap_value"],
+        "advantage": torch.full_like(t["value"], float("nan")),
+        "return_": torch.full_like(t["value"], float("nan")),
+    })
+
+
+def _oracle_adv(batch, gamma, lam):
+    adv, ret = np.empty_like(batch["value"]), np.empty_like(batch["value"])
+    fn = O.compute_discount_return if lam == 1.0 else O.compute_gae_advantage
+    fn(batch["reward"], batch["value"], batch["done"], batch["bootstrap_value"], gamma, lam, adv, ret)
+    return adv, ret
+
+
+@pytest.mark.parametrize("algo", ["serial", "chunked", "auto"])
+def test_advantage_matches_reference_golden(golden, algo):
+    from parllel_b200.transforms import EstimateAdvantage
+    g = golden("advantage")
+    for i in range(int(g["n_cases"])):
+        T, B, p, lam, gamma = g[f"{i}_meta"]
+        batch = {k: g[f"{i}_{k}"] for k in ("reward", "value", "done", "bootstrap_value")}
+        if algo == "chunked" and (int(B) % 16 != 0):
+            continue  # TMA needs 16-byte row strides; auto falls back to serial for these
+        tree = _device_tree(batch)
+        out = EstimateAdvantage(discount=gamma, gae_lambda=lam, algo=algo)(tree)
+        assert out is tree
+        assert_within_tolerance(tree["advantage"].cpu().numpy(), g[f"{i}_advantage"], what=f"adv case {i} {algo}")
+        assert_within_tolerance(tree["return_"].cpu().numpy(), g[f"{i}_return_"], what=f"ret case {i} {algo}")
+
+
+@pytest.mark.parametrize("lam", [0.95, 1.0])
+@pytest.mark.parametrize("T,B,p", [(1, 16, 0.1), (5, 48, 0.5), (63, 32, 0.0), (64, 64, 1.0), (65, 80, 0.02),
+                                   (200, 1000, 0.01), (1024, 512, 0.01), (130, 33, 0.05), (7, 1, 0.3)])
+def test_serial_is_bit_identical_to_oracle(T, B, p, lam):
+    from parllel_b200.transforms import EstimateAdvantage
+    batch = make_batch(np.random.default_rng(T * 1000 + B), T, B, p)
+    tree = _device_tree(batch)
+    EstimateAdvantage(0.99, lam, algo="serial")(tree)
+    adv, ret = _oracle_adv(batch, 0.99, lam)
+    assert np.array_equal(tree["advantage"].cpu().numpy(), adv)
+    assert np.array_equal(tree["return_"].cpu().numpy(), ret)
+
+
+@pytest.mark.parametrize("lam", [0.95, 1.0])
+@pytest.mark.parametrize("T,B,p", [(1, 16, 0.1), (5, 48, 0.5), (63, 32, 0.0), (64, 64, 1.0), (65, 80, 0.02),
+                                   (200, 1008, 0.01), (1024, 512, 0.01), (129, 4096, 0.01), (3000, 16, 0.001)])
+def test_chunked_within_tolerance_of_oracle(T, B, p, lam):
+    from parllel_b200.transforms import EstimateAdvantage
+    batch = make_batch(np.random.default_rng(T * 1000 + B + 1), T, B, p)
+    tree = _device_tree(batch)
+    EstimateAdvantage(0.99, lam, algo="chunked")(tree)
+    adv, ret = _oracle_adv(batch, 0.99, lam)
+    assert_within_tolerance(tree["advantage"].cpu().numpy(), adv, what="advantage")
+    assert_within_tolerance(tree["return_"].cpu().numpy(), ret, what="return_")
+
+
+def test_strided_views_into_padded_bases():
+    """done is a window into a [T+2, B] padded base (patterns.py:191-198): row stride == B but an
+    offset base pointer; value/advantage as column slices of wider arrays (ld > B)."""
+    from parllel_b200 import ArrayDict, DeviceArray
+    from parllel_b200.transforms import EstimateAdvantage
+    T, B = 96, 64
+    batch = make_batch(np.random.default_rng(5), T, B, 0.05)
+    done = DeviceArray((T, B), np.bool_, padding=1)
+    done[...] = batch["done"]
+    wide_v = torch.zeros((T, 2 * B), device="cuda")
+    wide_v[:, B:] = torch.from_numpy(batch["value"]).cuda()
+    wide_a = torch.zeros((T, 3 * B), device="cuda")
+    for algo in ("serial", "chunked"):
+        tree = ArrayDict({
+            "reward": torch.from_numpy(batch["reward"]).cuda(), "done": done,
+            "agent_info": {"value": wide_v[:, B:]}, "bootstrap_value": torch.from_numpy(batch["bootstrap_value"]).cuda(),
+            "advantage": wide_a[:, B:2 * B], "return_": torch.zeros((T, B), device="cuda"),
+        })
+        EstimateAdvantage(0.99, 0.95, algo=algo)(tree)
+        adv, ret = _oracle_adv(batch, 0.99, 0.95)
+        assert_within_tolerance(wide_a[:, B:2 * B].cpu().numpy(), adv, what=algo)
+        assert_within_tolerance(tree["return_"].cpu().numpy(), ret, what=algo)
+        assert float(wide_a[:, :B].abs().max()) == 0.0 and float(wide_a[:, 2 * B:].abs().max()) == 0.0
+
+
+def test_multi_agent_trailing_axis_matches_golden(golden):
+    from parllel_b200.transforms import EstimateAdvantage
+    g = golden("multi_advantage")
+    for i in range(int(g["n_cases"])):
+        T, B, N, lam, gamma = g[f"{i}_meta"]
+        batch = {k: g[f"{i}_{k}"] for k in ("reward", "value", "done", "bootstrap_value")}
+        tree = _device_tree(batch)
+        EstimateAdvantage(gamma, lam)(tree)
+        assert_within_tolerance(tree["advantage"].cpu().numpy(), g[f"{i}_advantage"], what=f"case {i}")
+        assert_within_tolerance(tree["return_"].cpu().numpy(), g[f"{i}_return_"], what=f"case {i}")
+
+
+def test_host_leaves_are_staged_and_written_back():
+    """Drop-in path: numpy leaves in, CUDA kernels compute, results land in the caller's arrays."""
+    from parllel_b200 import ArrayDict
+    from parllel_b200.transforms import EstimateAdvantage
+    batch = make_batch(np.random.default_rng(3), 128, 16, 0.01)
+    tree = ArrayDict({"reward": batch["reward"], "done": batch["done"], "agent_info": {"value": batch["value"]},
+                      "bootstrap_value": batch["bootstrap_value"],
+                      "advantage": np.zeros_like(batch["value"]), "return_": np.zeros_like(batch["value"])})
+    EstimateAdvantage(0.99, 0.95, algo="serial")(tree)
+    adv, ret = _oracle_adv(batch, 0.99, 0.95)
+    assert np.array_equal(tree["advantage"], adv) and np.array_equal(tree["return_"], ret)
+
+
+@pytest.mark.parametrize("algo", ["serial", "chunked"])
+@pytest.mark.parametrize("T,B,p", [(1, 16, 0.5), (64, 64, 0.1), (65, 48, 0.02), (500, 1024, 0.01), (77, 5, 0.1)])
+def test_past_discount_return(T, B, p, algo):
+    from parllel_b200 import _lib
+    if algo == "chunked" and B % 16:
+        pytest.skip("TMA needs 16-byte row strides")
+    rng = np.random.default_rng(T + B)
+    reward = rng.standard_normal((T, B)).astype(np.float32)
+    done = rng.random((T, B)) < p
+    prev_r = rng.standard_normal(B).astype(np.float32)
+    prev_d = rng.random(B) < 0.3
+    ref = np.empty_like(reward)
+    O.compute_past_discount_return(reward, done, prev_r, prev_d, 0.99, ref)
+    r, d = torch.from_numpy(reward).cuda(), torch.from_numpy(done).cuda()
+    pr, pd = torch.from_numpy(prev_r).cuda(), torch.from_numpy(prev_d).cuda()
+    out = torch.full((T, B), float("nan"), device="cuda")
+    lib = _lib.load()
+    rc = lib.plb_compute_past_discount_return_f32(r.data_ptr(), B, d.data_ptr(), B, pr.data_ptr(), pd.data_ptr(),
+                                                  out.data_ptr(), B, T, B, 0.99,
+                                                  _lib.ALGO_SERIAL if algo == "serial" else _lib.ALGO_CHUNKED,
+                                                  torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc)
+    if algo == "serial":
+        assert np.array_equal(out.cpu().numpy(), ref)
+    else:
+        assert_within_tolerance(out.cpu().numpy(), ref)
+
+
+def test_c1_full_size_properties():
+    """BASELINE config C1 (T=1024, B=4096): serial == oracle bit for bit; chunked within tolerance;
+    size-independent properties: an all-done mask decouples every step, linearity in reward."""
+    from parllel_b200.transforms import EstimateAdvantage
+    T, B = 1024, 4096
+    batch = make_batch(np.random.default_rng(1), T, B, 0.01)
+    adv_ref, ret_ref = _oracle_adv(batch, 0.99, 0.95)
+    tree = _device_tree(batch)
+    EstimateAdvantage(0.99, 0.95, algo="serial")(tree)
+    assert np.array_equal(tree["advantage"].cpu().numpy(), adv_ref)
+    tree2 = _device_tree(batch)
+    EstimateAdvantage(0.99, 0.95, algo="chunked")(tree2)
+    assert_within_tolerance(tree2["advantage"].cpu().numpy(), adv_ref, what="C1 advantage")
+    assert_within_tolerance(tree2["return_"].cpu().numpy(), ret_ref, what="C1 return_")
+    # all done: advantage[t] = reward[t] - value[t] exactly
+    b3 = dict(batch, done=np.ones((T, B), bool))
+    tree3 = _device_tree(b3)
+    EstimateAdvantage(0.99, 0.95, algo="chunked")(tree3)
+    assert np.array_equal(tree3["advantage"].cpu().numpy(), batch["reward"] - batch["value"])
+    # linearity: scaling reward, value and bootstrap by 2 scales the advantage by exactly 2
+    b4 = dict(batch, reward=batch["reward"] * 2, value=batch["value"] * 2, bootstrap_value=batch["bootstrap_value"] * 2)
+    tree4 = _device_tree(b4)
+    EstimateAdvantage(0.99, 0.95, algo="chunked")(tree4)
+    assert np.array_equal(tree4["advantage"].cpu().numpy(), 2 * tree2["advantage"].cpu().numpy())
+
+
+def test_empty_batch_is_a_noop():
+    from parllel_b200 import _lib
+    lib = _lib.load()
+    rc = lib.plb_compute_gae_advantage_f32(0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 16, 1, 0.99, 0.95, 0, 0)
+    assert rc == 0
+
+
+def test_bad_arguments_fail_loudly():
+    from parllel_b200 import _lib
+    lib = _lib.load()
+    x = torch.zeros((4, 8), device="cuda")
+    rc = lib.plb_compute_gae_advantage_f32(x.data_ptr(), 4, x.data_ptr(), 8, x.data_ptr(), 8, x.data_ptr(),
+                                           x.data_ptr(), 8, x.data_ptr(), 8, 4, 8, 1, 0.99, 0.95, 0, 0)
+    assert rc == -1 and b"stride" in lib.plb_last_error()
+    with pytest.raises(_lib.PlbError):
+        _lib.check(rc, "gae")

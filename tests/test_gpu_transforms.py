@@ -1,0 +1,251 @@
+"""GPU parity: NormalizeRewards / ClipRewards / NormalizeAdvantage / NormalizeObservations and the
+running statistics, against the reference's golden outputs and the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as O
+from tests.util import assert_within_tolerance, make_batch
+
+pytestmark = pytest.mark.gpu
+
+
+def _make_device_tree(T, B, with_valid):
+    """Device mirror of the sample tree parllel/patterns.py allocates (done / past_return padded)."""
+    from parllel_b200 import ArrayDict, DeviceArray
+    tree = ArrayDict({
+        "reward": DeviceArray((T, B), np.float32),
+        "done": DeviceArray((T, B), np.bool_, padding=1),
+        "agent_info": {"value": DeviceArray((T, B), np.float32)},
+        "bootstrap_value": torch.zeros(B, device="cuda"),
+        "advantage": DeviceArray((T, B), np.float32),
+        "return_": DeviceArray((T, B), np.float32),
+        "past_return": DeviceArray((T, B), np.float32, padding=1),
+    })
+    if with_valid:
+        tree["valid"] = DeviceArray((T, B), np.bool_)
+    return tree
+
+
+@pytest.mark.parametrize("name", ["pipeline_c0", "pipeline_valid", "pipeline_lambda1"])
+@pytest.mark.parametrize("leaves", ["device_array", "plain_tensor"])
+def test_batch_transform_pipeline_matches_reference(golden, name, leaves):
+    """NormalizeRewards -> ClipRewards -> EstimateAdvantage -> NormalizeAdvantage over consecutive
+    rotating batches (examples/cartpole/train_ppo.py:101-121), carry rows included."""
+    from parllel_b200 import ArrayDict
+    from parllel_b200.transforms import ClipRewards, EstimateAdvantage, NormalizeAdvantage, NormalizeRewards
+    g = golden(name)
+    T, B, p_done, n_batches, with_valid, lam, clip_lo, clip_hi, init_count = g["meta"]
+    T, B, with_valid = int(T), int(B), bool(with_valid)
+    tree = _make_device_tree(T, B, with_valid)
+    if leaves == "plain_tensor":  # no padding anywhere: the transform carries the previous rows itself
+        tree = ArrayDict({k: (v if isinstance(v, (torch.Tensor, ArrayDict)) else v.tensor) for k, v in tree.items()})
+        tree["agent_info"] = ArrayDict({"value": tree["agent_info"]["value"].tensor})
+    transforms = [
+        NormalizeRewards(tree, discount=0.99, initial_count=None if init_count < 0 else init_count),
+        ClipRewards(reward_min=clip_lo, reward_max=clip_hi),
+        EstimateAdvantage(discount=0.99, gae_lambda=lam),
+        NormalizeAdvantage(tree),
+    ]
+    for it in range(int(n_batches)):
+        if leaves == "device_array":
+            tree.rotate()
+        tree["reward"][...] = torch.from_numpy(g[f"b{it}_in_reward"]).cuda()
+        tree["agent_info"]["value"][...] = torch.from_numpy(g[f"b{it}_in_value"]).cuda()
+        tree["done"][...] = torch.from_numpy(g[f"b{it}_in_done"]).cuda()
+        tree["bootstrap_value"][...] = torch.from_numpy(g[f"b{it}_in_bootstrap_value"]).cuda()
+        if with_valid:
+            tree["valid"][...] = torch.from_numpy(g[f"b{it}_in_valid"]).cuda()
+        if leaves == "device_array":  # rotate() must have carried the previous rows into the padding
+            assert np.array_equal(tree["past_return"][-1].cpu().numpy(), g[f"b{it}_in_prev_past_return"]) or it > 0
+            assert np.array_equal(tree["done"][-1].cpu().numpy(), g[f"b{it}_in_prev_done"])
+        for tf in transforms:
+            out = tf(tree)
+            assert out is tree
+        for k in ("past_return", "reward", "return_", "advantage"):
+            assert_within_tolerance(np.asarray(tree[k].cpu() if isinstance(tree[k], torch.Tensor) else tree[k]),
+                                    g[f"b{it}_out_{k}"], what=f"{name} batch {it} {k}")
+        st = transforms[0].return_statistics
+        np.testing.assert_allclose([st.mean, st.var, st.count], g[f"b{it}_out_stats"], rtol=2e-6)
+
+
+@pytest.mark.parametrize("name", ["norm_obs", "norm_obs_valid"])
+def test_normalize_observations_matches_reference(golden, name):
+    from parllel_b200 import ArrayDict, DeviceArray
+    from parllel_b200.transforms import NormalizeObservations
+    g = golden(name)
+    B, n_steps, with_valid, init_count = g["meta"]
+    B, n_steps = int(B), int(n_steps)
+    shape = tuple(int(x) for x in g["obs_shape"])
+    tree = ArrayDict({"observation": DeviceArray((n_steps, B), np.float32, feature_shape=shape, padding=1)})
+    tree["observation"][...] = torch.from_numpy(g["in_observation"]).cuda()
+    if with_valid:
+        tree["valid"] = DeviceArray((n_steps, B), np.bool_)
+        tree["valid"][...] = torch.from_numpy(g["in_valid"]).cuda()
+    tf = NormalizeObservations(tree, obs_shape=shape, initial_count=None if init_count < 0 else init_count)
+    for t in range(n_steps):
+        tf(tree[t])  # step transform on sample_tree[t]
+        np.testing.assert_allclose(tf.obs_statistics.mean, g[f"s{t}_mean"], rtol=1e-6, atol=1e-7)
+        np.testing.assert_allclose(tf.obs_statistics.var, g[f"s{t}_var"], rtol=2e-6)
+        np.testing.assert_allclose(tf.obs_statistics.count, g[f"s{t}_count"], rtol=1e-15)
+    got = np.asarray(tree["observation"])
+    np.testing.assert_allclose(got, g["out_observation"], rtol=1e-5, atol=1e-5)
+
+
+def test_normalize_observations_batched_entry_equals_stepwise(golden):
+    from parllel_b200.transforms import NormalizeObservations
+    g = golden("norm_obs")
+    shape = tuple(int(x) for x in g["obs_shape"])
+    obs = torch.from_numpy(g["in_observation"]).cuda()
+    tf = NormalizeObservations({"observation": obs}, obs_shape=shape, initial_count=10000)
+    tf.normalize_batch(obs)
+    np.testing.assert_allclose(obs.cpu().numpy(), g["out_observation"], rtol=1e-5, atol=1e-5)
+
+
+def test_normalize_advantage_multi_agent_matches_golden(golden):
+    from parllel_b200.transforms import NormalizeAdvantage
+    g = golden("multi_advantage")
+    for i in range(int(g["n_cases"])):
+        adv = torch.from_numpy(g[f"{i}_advantage"]).cuda()
+        tree = {"advantage": adv}
+        NormalizeAdvantage(tree)(tree)
+        assert_within_tolerance(adv.cpu().numpy(), g[f"{i}_norm_advantage"], what=f"case {i}")
+
+
+@pytest.mark.parametrize("shape", [(1, 3), (7, 5), (128, 16), (333, 77), (1024, 4096)])
+@pytest.mark.parametrize("masked", [False, True])
+def test_batch_moments_vs_numpy_float64(shape, masked):
+    from parllel_b200 import _lib
+    rng = np.random.default_rng(shape[0] + shape[1])
+    x = (100.0 + 3.0 * rng.standard_normal(shape)).astype(np.float32)  # large mean: cancellation stress
+    valid = rng.random(shape) < 0.6 if masked else None
+    if masked:
+        valid[0, 0] = True
+    lib = _lib.load()
+    xd = torch.from_numpy(x).cuda()
+    vd = torch.from_numpy(valid).cuda() if masked else None
+    out = torch.zeros(3, dtype=torch.float64, device="cuda")
+    ws = torch.zeros(lib.plb_batch_moments_workspace_bytes(), dtype=torch.uint8, device="cuda")
+    for _ in range(2):  # second call checks the workspace is left reusable
+        _lib.check(lib.plb_batch_moments_f32(xd.data_ptr(), shape[1], shape[0], shape[1],
+                                             vd.data_ptr() if masked else 0, shape[1], out.data_ptr(),
+                                             ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream))
+    n, mean, m2 = out.cpu().numpy()
+    sel = x[valid].astype(np.float64) if masked else x.astype(np.float64).ravel()
+    assert n == sel.size
+    np.testing.assert_allclose(mean, sel.mean(), rtol=1e-13)
+    np.testing.assert_allclose(m2 / n, sel.var(), rtol=1e-11)
+
+
+@pytest.mark.parametrize("rows,cols", [(1, 4), (5, 3), (64, 192), (1024, 21168), (100, 10)])
+def test_column_moments_vs_numpy_float64(rows, cols):
+    from parllel_b200 import _lib
+    rng = np.random.default_rng(rows + cols)
+    x = (5.0 + 3.0 * rng.standard_normal((rows, cols))).astype(np.float32)
+    valid = rng.random(rows) < 0.7
+    valid[0] = True
+    lib = _lib.load()
+    xd, vd = torch.from_numpy(x).cuda(), torch.from_numpy(valid).cuda()
+    cnt = torch.zeros(1, dtype=torch.float64, device="cuda")
+    mean = torch.zeros(cols, dtype=torch.float64, device="cuda")
+    m2 = torch.zeros(cols, dtype=torch.float64, device="cuda")
+    ws = torch.zeros(lib.plb_column_moments_workspace_bytes(rows, cols), dtype=torch.uint8, device="cuda")
+    for use_valid in (False, True):
+        _lib.check(lib.plb_column_moments_f32(xd.data_ptr(), cols, rows, cols, vd.data_ptr() if use_valid else 0,
+                                              cnt.data_ptr(), mean.data_ptr(), m2.data_ptr(), ws.data_ptr(), ws.numel(),
+                                              torch.cuda.current_stream().cuda_stream))
+        sel = x[valid] if use_valid else x
+        assert float(cnt) == sel.shape[0]
+        np.testing.assert_allclose(mean.cpu().numpy(), sel.astype(np.float64).mean(0), rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(m2.cpu().numpy() / sel.shape[0], sel.astype(np.float64).var(0), rtol=1e-10, atol=1e-12)
+
+
+def test_running_mean_std_reference_unit_test_on_device():
+    """The reference's own RunningMeanStd test (transforms/tests/test_running_mean_std.py:40-59),
+    a representative subset of its grid, run through the device implementation."""
+    from parllel_b200.transforms import RunningMeanStd
+    for batch_size, n_batches in [(1, 100), (10, 100), (100, 10), (100, 1)]:
+        for mu, sd in [(0., 1.0), (5., 5.), (100., 5.), (100., 200.)]:
+            rng = np.random.default_rng(seed=42)
+            stats = RunningMeanStd(shape=(1,))
+            all_data = np.zeros((batch_size * n_batches, 1), np.float64)
+            for i in range(n_batches):
+                batch = rng.normal(mu, sd, size=(batch_size, 1))
+                stats.update(torch.from_numpy(batch.astype(np.float32)).cuda(), f32_flow=False)
+                all_data[i * batch_size:(i + 1) * batch_size] = batch.astype(np.float32)
+            assert np.allclose(np.mean(all_data, axis=0), stats.mean)
+            assert np.allclose(np.var(all_data, axis=0), stats.var, rtol=1e-3)
+            assert np.allclose(all_data.shape[0], stats.count, atol=1e-2)
+
+
+def test_update_from_moments_bit_exact_vs_oracle():
+    """float64 Chan merge: same operation order as running_mean_std.py:23-30 -> identical bits."""
+    from parllel_b200 import _lib
+    rng = np.random.default_rng(0)
+    n = 1000
+    lib = _lib.load()
+    for f32 in (False, True):
+        bm = rng.standard_normal(n) * 5
+        bv = rng.random(n) * 9 + 0.1
+        if f32:
+            bm, bv = bm.astype(np.float32).astype(np.float64), bv.astype(np.float32).astype(np.float64)
+        bn = 48.0
+        stats = O.RunningMeanStd((n,), initial_count=3.5)
+        stats.mean[:] = rng.standard_normal(n)
+        stats.var[:] = rng.random(n) + 0.5
+        mean0, var0 = stats.mean.copy(), stats.var.copy()
+        stats.update_from_moments(bm.astype(np.float32) if f32 else bm, bv.astype(np.float32) if f32 else bv, bn)
+        d = lambda a: torch.from_numpy(np.ascontiguousarray(a, np.float64)).cuda()
+        mean, var, cnt = d(mean0), d(var0), d(np.array([3.5]))
+        bcnt, bmean, bm2 = d(np.array([bn])), d(bm), d(bv * bn)
+        _lib.check(lib.plb_update_from_moments_f64(bcnt.data_ptr(), bmean.data_ptr(), bm2.data_ptr(), mean.data_ptr(),
+                                                   var.data_ptr(), cnt.data_ptr(), n,
+                                                   _lib.MOMENTS_F32_FLOW if f32 else 0,
+                                                   torch.cuda.current_stream().cuda_stream))
+        assert np.array_equal(mean.cpu().numpy(), stats.mean)
+        if not f32:  # bv*bn/bn is not always exactly bv, so only the float64 flow can be bit-compared on var
+            np.testing.assert_allclose(var.cpu().numpy(), stats.var, rtol=1e-15)
+        else:
+            np.testing.assert_allclose(var.cpu().numpy(), stats.var, rtol=1e-7)
+        assert float(cnt) == float(stats.count)
+
+
+def test_clip_rewards_semantics():
+    from parllel_b200.transforms import ClipRewards
+    with pytest.raises(ValueError):
+        ClipRewards()
+    x = np.random.default_rng(0).standard_normal((37, 19)).astype(np.float32) * 4
+    for lo, hi in [(-1.0, None), (None, 2.0), (-0.5, 0.25)]:
+        t = {"reward": torch.from_numpy(x.copy()).cuda()}
+        ClipRewards(lo, hi)(t)
+        assert np.array_equal(t["reward"].cpu().numpy(), np.clip(x, lo, hi))
+
+
+def test_constructor_errors_match_reference():
+    from parllel_b200.transforms import NormalizeObservations, NormalizeRewards
+    tree = {"reward": torch.zeros(2, 2), "observation": torch.zeros(2, 2, 3)}
+    with pytest.raises(ValueError):
+        NormalizeRewards(tree, discount=0.99, initial_count=0.5)
+    with pytest.raises(ValueError):
+        NormalizeObservations(tree, obs_shape=(3,), initial_count=0.0)
+    with pytest.raises(NotImplementedError):
+        NormalizeObservations({"observation": {"a": 1}}, obs_shape=(3,))
+    with pytest.raises(NotImplementedError):
+        NormalizeRewards({"reward": {"a": 1}}, discount=0.9)
+
+
+def test_c2_shape_observation_step_vs_oracle():
+    """BASELINE config C2 shape (B=1024, obs 3x84x84), two dependent steps, vs the oracle."""
+    from parllel_b200.transforms import NormalizeObservations
+    rng = np.random.default_rng(2)
+    shape = (3, 84, 84)
+    obs = (5.0 + 3.0 * rng.standard_normal((2, 1024) + shape)).astype(np.float32)
+    ref = obs.copy()
+    stats = O.RunningMeanStd(shape, initial_count=10000)
+    for t in range(2):
+        O.normalize_observations_step(ref[t], stats)
+    d = torch.from_numpy(obs).cuda()
+    tf = NormalizeObservations({"observation": d}, obs_shape=shape, initial_count=10000)
+    tf.normalize_batch(d)
+    np.testing.assert_allclose(d.cpu().numpy(), ref, rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(tf.obs_statistics.var, stats.var, rtol=5e-6)
