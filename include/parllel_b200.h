@@ -66,6 +66,12 @@ PLB_API int plb_version(void);
 PLB_API const char *plb_last_error(void);
 /* Number of SMs of the current device (grid sizing); <0 on error. */
 PLB_API int plb_sm_count(void);
+/* Tuning / diagnostics knobs (process-wide; used by tools/ and the tests, not by the transforms).
+ *   key 0: rows per warp per tile of the chunked scan (8 or 16; default 16 when one CTA per SM)
+ *   key 1: 1 = float32 affine maps in the chunked scan (default 0 = float64) */
+#define PLB_TUNE_CHUNK_ROWS 0
+#define PLB_TUNE_CHUNK_F32 1
+PLB_API int plb_set_tuning(int key, int value);
 
 /* ------------------------------------------------------------------------------------
  * EstimateAdvantage            parllel/transforms/advantage.py:36-57 (compute_gae_advantage)

@@ -31,6 +31,7 @@ _SIGNATURES = {
     "plb_version": ([], c_int),
     "plb_last_error": ([], ctypes.c_char_p),
     "plb_sm_count": ([], c_int),
+    "plb_set_tuning": ([c_int, c_int], c_int),
     "plb_compute_gae_advantage_f32": (
         [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64,
          c_int64, c_int64, c_int64, c_double, c_double, c_int, c_void_p], c_int),

@@ -20,6 +20,8 @@
 #include <cuda.h>
 #include <math.h>
 
+#include <type_traits>
+
 #include "plb_common.cuh"
 #include "plb_scan_shared.cuh"
 
@@ -171,24 +173,28 @@ scan_forward_serial_kernel(const float *__restrict__ reward, int64_t ld_r,
 namespace chunked {
 
 constexpr int W = 32;        // columns per strip (one lane per column)
-constexpr int TC = 64;       // rows per tile
-constexpr int NWARPS = 8;    // warps per CTA
-constexpr int R = TC / NWARPS;
+constexpr int NWARPS = 8;    // warps per CTA; warp w owns rows [w*R, (w+1)*R) of a tile
 constexpr int THREADS = NWARPS * 32;
-constexpr int MAX_STAGES = 8;
+constexpr int MAX_STAGES = 12;
 
-// one pipeline stage: three TMA boxes
+// one input pipeline stage: three TMA boxes of TC = NWARPS*R rows x 32 columns
+template <int R>
 struct __align__(128) Stage {
-    float r[TC][W];
-    float v[TC][W];
-    uint8_t d[TC][W];
+    float r[NWARPS * R][W];
+    float v[NWARPS * R][W];
+    uint8_t d[NWARPS * R][W];
 };
-constexpr uint32_t STAGE_TX_REVERSE = sizeof(float) * TC * W * 2 + TC * W;  // r + v + d
-constexpr uint32_t STAGE_TX_FORWARD = sizeof(float) * TC * W + TC * W;      // r + d
 
+// one output staging buffer (TMA-stored to global; the TMA clips rows/columns outside the tensor)
+template <int R, int N_OUT>
+struct __align__(128) OutTile {
+    float o[N_OUT][NWARPS * R][W];
+};
+
+template <typename ACC>
 struct Shared {
-    double aggA[2][NWARPS][W];
-    double aggC[2][NWARPS][W];
+    ACC aggA[2][NWARPS][W];
+    ACC aggC[2][NWARPS][W];
     float halo[2][W];
     unsigned long long full[MAX_STAGES];
 };
@@ -197,8 +203,6 @@ struct Params {
     const float *boot;            // reverse: bootstrap value [B]
     const float *prev_ret;        // forward: previous return [B]
     const uint8_t *prev_done;     // forward: previous done [B]
-    float *out0; int64_t ld0;     // reverse: advantage   | forward: past_return
-    float *out1; int64_t ld1;     // reverse: return_
     int64_t T, B;
     double gamma, lambda;
     int n_stages;
@@ -207,206 +211,275 @@ struct Params {
     const double *reward_var;     // device float64 running variance, or NULL
     double reward_eps;
     float clip_lo, clip_hi;       // -inf / +inf when absent
-    int has_pre;
-    float *reward_out; int64_t ld_reward_out;  // transformed reward written back (may be NULL)
     // optional fused moments of out0
     const uint8_t *valid; int64_t ld_valid;
-    MomentsTail tail;             // moments_out == NULL -> off
+    MomentsTail tail;
 };
 
-// MODE 0: GAE, 1: discounted return (both reverse), 2: past return (forward)
-template <int MODE>
+struct TensorMaps {
+    CUtensorMap r, v, d;      // inputs
+    CUtensorMap o0, o1, o2;   // outputs: (advantage | past_return), return_, transformed reward
+    // Reverse scans align tiles to the END of the batch, so the earliest tile may start at a
+    // negative row.  TMA loads zero-fill there, but a TMA STORE may not start out of bounds:
+    // that ragged tile is stored through maps whose box is only T % TC rows tall, from row 0.
+    CUtensorMap o0_rag, o1_rag, o2_rag;
+};
+
+__device__ __forceinline__ float to_f32(double x) { return __double2float_rn(x); }
+__device__ __forceinline__ float to_f32(float x) { return x; }
+
+// MODE 0: GAE, 1: discounted return (both reverse), 2: past return (forward).
+// ACC: arithmetic type of the affine maps (double = default; float = fast variant).
+// Output slots: MODE 0: o0 = advantage, o1 = return_; MODE 1: same; MODE 2: o0 = past_return;
+//               HAS_PRE adds the transformed reward as the last slot.
+template <int MODE, typename ACC, int R, bool HAS_PRE, bool HAS_STATS>
 __global__ void __launch_bounds__(THREADS)
-scan_chunked_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtensorMap tm_v,
-                    const __grid_constant__ CUtensorMap tm_d, const Params p)
+scan_chunked_kernel(const __grid_constant__ TensorMaps tm, const Params p)
 {
+    constexpr int TC = NWARPS * R;
+    constexpr bool REVERSE = (MODE != 2);
+    constexpr int N_OUT = (REVERSE ? 2 : 1) + (HAS_PRE ? 1 : 0);
+    constexpr int PRE_SLOT = N_OUT - 1;
+    constexpr uint32_t TX_BYTES = REVERSE ? (sizeof(float) * TC * W * 2 + TC * W) : (sizeof(float) * TC * W + TC * W);
+    using StageT = Stage<R>;
+    using OutT = OutTile<R, N_OUT>;
+    using SharedT = Shared<ACC>;
+
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    Stage *stages = reinterpret_cast<Stage *>(smem_raw);
-    Shared *sh = reinterpret_cast<Shared *>(smem_raw + sizeof(Stage) * p.n_stages);
+    StageT *stages = reinterpret_cast<StageT *>(smem_raw);
+    OutT *outs = reinterpret_cast<OutT *>(smem_raw + sizeof(StageT) * p.n_stages);
+    SharedT *sh = reinterpret_cast<SharedT *>(smem_raw + sizeof(StageT) * p.n_stages + 2 * sizeof(OutT));
     __shared__ Moments red_scratch[32];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr bool REVERSE = (MODE != 2);
-    const uint32_t tx_bytes = REVERSE ? STAGE_TX_REVERSE : STAGE_TX_FORWARD;
+    const int n_stages = p.n_stages, n_chunks = p.n_chunks, n_strips = p.n_strips;
+    const int64_t T = p.T;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < p.n_stages; ++s) mbar_init(&sh->full[s], 1);
+        for (int s = 0; s < n_stages; ++s) mbar_init(&sh->full[s], 1);
         fence_mbar_init();
     }
     __syncthreads();
 
-    // this CTA's item sequence: strips blockIdx.x, +gridDim.x, ...; chunks in scan order
-    const int my_strips = (p.n_strips - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    const int64_t Q = (int64_t)my_strips * p.n_chunks;
-
-    auto issue = [&](int64_t q) {
-        const int s = (int)(q % p.n_stages);
-        const int strip = (int)blockIdx.x + (int)(q / p.n_chunks) * (int)gridDim.x;
-        const int k = (int)(q % p.n_chunks);
-        const int c0 = strip * W;
-        int t0;
-        if (REVERSE) t0 = (int)p.T - (k + 1) * TC;   // tiles aligned to the END of the batch
-        else t0 = k * TC;                            // tiles aligned to the START
-        mbar_arrive_expect_tx(&sh->full[s], tx_bytes);
-        tma_load_2d(&stages[s].r[0][0], &tm_r, c0, t0, &sh->full[s]);
+    // ---- producer state (thread 0 only): next tile to request -------------------------
+    int iss_strip = blockIdx.x, iss_chunk = 0, iss_stage = 0;
+    auto issue_one = [&]() {
+        const int c0 = iss_strip * W;
+        const int t0 = REVERSE ? (int)T - (iss_chunk + 1) * TC : iss_chunk * TC;
+        unsigned long long *bar = &sh->full[iss_stage];
+        StageT &S = stages[iss_stage];
+        mbar_arrive_expect_tx(bar, TX_BYTES);
+        tma_load_2d(&S.r[0][0], &tm.r, c0, t0, bar);
         if (REVERSE) {
-            tma_load_2d(&stages[s].v[0][0], &tm_v, c0, t0, &sh->full[s]);
-            tma_load_2d(&stages[s].d[0][0], &tm_d, c0, t0, &sh->full[s]);
+            tma_load_2d(&S.v[0][0], &tm.v, c0, t0, bar);
+            tma_load_2d(&S.d[0][0], &tm.d, c0, t0, bar);
         } else {
-            tma_load_2d(&stages[s].d[0][0], &tm_d, c0, t0 - 1, &sh->full[s]);  // done[t-1]
+            tma_load_2d(&S.d[0][0], &tm.d, c0, t0 - 1, bar);  // done[t-1]
         }
+        if (++iss_chunk == n_chunks) { iss_chunk = 0; iss_strip += gridDim.x; }
+        if (++iss_stage == n_stages) iss_stage = 0;
     };
-
+    // ---- store state (thread 0 only): the tile whose outputs sit in outs[par ^ 1] -----
+    bool st_pending = false;
+    int st_c0 = 0, st_t0 = 0;
+    auto store_tile = [&](int buf) {
+        if (REVERSE && st_t0 < 0) {
+            const int skip = -st_t0;  // rows of the staging tile that lie before t = 0
+            tma_store_2d(&tm.o0_rag, &outs[buf].o[0][skip][0], st_c0, 0);
+            tma_store_2d(&tm.o1_rag, &outs[buf].o[1][skip][0], st_c0, 0);
+            if (HAS_PRE) tma_store_2d(&tm.o2_rag, &outs[buf].o[PRE_SLOT][skip][0], st_c0, 0);
+        } else {
+            tma_store_2d(&tm.o0, &outs[buf].o[0][0][0], st_c0, st_t0);
+            if (REVERSE) tma_store_2d(&tm.o1, &outs[buf].o[1][0][0], st_c0, st_t0);
+            if (HAS_PRE) tma_store_2d(&tm.o2, &outs[buf].o[PRE_SLOT][0][0], st_c0, st_t0);
+        }
+        tma_store_commit();
+    };
     if (threadIdx.x == 0) {
-        tma_prefetch_desc(&tm_r);
-        if (REVERSE) tma_prefetch_desc(&tm_v);
-        tma_prefetch_desc(&tm_d);
-        for (int64_t q = 0; q < Q && q < p.n_stages; ++q) issue(q);
+        tma_prefetch_desc(&tm.r);
+        if (REVERSE) tma_prefetch_desc(&tm.v);
+        tma_prefetch_desc(&tm.d);
+        for (int s = 0; s < n_stages && iss_strip < n_strips; ++s) issue_one();
+        tma_prefetch_desc(&tm.o0);
+        if (REVERSE) tma_prefetch_desc(&tm.o1);
+        if (HAS_PRE) tma_prefetch_desc(&tm.o2);
     }
 
-    // fused reward transform constants
+    const ACC gamma = (ACC)p.gamma;
+    const ACC gl = (ACC)(p.gamma * p.lambda);
     double inv_denom = 1.0;
-    if (p.has_pre && p.reward_var != nullptr) inv_denom = 1.0 / sqrt(*p.reward_var + p.reward_eps);
-    const double gl = p.gamma * p.lambda;
+    float clip_lo = 0.f, clip_hi = 0.f;
+    if (HAS_PRE) {
+        if (p.reward_var != nullptr) inv_denom = 1.0 / sqrt(*p.reward_var + p.reward_eps);
+        clip_lo = p.clip_lo;
+        clip_hi = p.clip_hi;
+    }
 
-    PivotAcc acc;
-    acc.init();
+    Moments acc;  // fused statistics of out0 (HAS_STATS)
+    acc.n = 0.0; acc.mean = 0.0; acc.m2 = 0.0;
 
-    double carry = 0.0;      // scan value just outside the tile (strip-level carry), per lane
-    for (int64_t q = 0; q < Q; ++q) {
-        const int s = (int)(q % p.n_stages);
-        const uint32_t parity = (uint32_t)((q / p.n_stages) & 1);
-        const int strip = (int)blockIdx.x + (int)(q / p.n_chunks) * (int)gridDim.x;
-        const int k = (int)(q % p.n_chunks);
+    int stage = 0, par = 0;
+    uint32_t phase = 0;
+    const int i0 = warp * R;
+    for (int strip = blockIdx.x; strip < n_strips; strip += gridDim.x) {
         const int64_t col = (int64_t)strip * W + lane;
         const bool col_ok = col < p.B;
-        const int par = (int)(q & 1);
-        int64_t t0;
-        if (REVERSE) t0 = p.T - (int64_t)(k + 1) * TC;
-        else t0 = (int64_t)k * TC;
-        const Stage &S = stages[s];
+        ACC carry;  // scan value just outside the current tile, per column
+        if (MODE == 0) carry = (ACC)0;
+        else if (MODE == 1) carry = col_ok ? (ACC)p.boot[col] : (ACC)0;
+        else carry = col_ok ? (ACC)p.prev_ret[col] : (ACC)0;
+        float halo_v = 0.f;  // GAE: value[t+1] for the last row of the first tile = bootstrap value
+        if (MODE == 0 && warp == NWARPS - 1) halo_v = col_ok ? p.boot[col] : 0.f;
+        bool first_prev_done = false;
+        if (MODE == 2 && warp == 0) first_prev_done = col_ok ? (p.prev_done[col] != 0) : false;
 
-        mbar_wait(&sh->full[s], parity);
+        for (int k = 0; k < n_chunks; ++k) {
+            const int64_t t0 = REVERSE ? T - (int64_t)(k + 1) * TC : (int64_t)k * TC;
+            const StageT &S = stages[stage];
+            OutT &O = outs[par];
+            mbar_wait(&sh->full[stage], phase);
 
-        double A[R], C[R];
-        float vreg[R];
-        (void)vreg;
+            ACC A[R], C[R];
+            float vreg[R];
+            (void)vreg;
 
-        if (REVERSE) {
-            if (k == 0) carry = (MODE == 1 && col_ok) ? (double)p.boot[col] : 0.0;
-            const int i_hi = (warp + 1) * R - 1;
-            // value[t+1] for the warp's last row
-            double vnext;
-            if (MODE == 0) {
-                if (i_hi + 1 < TC) vnext = (double)S.v[i_hi + 1][lane];
-                else if (k == 0) vnext = col_ok ? (double)p.boot[col] : 0.0;
-                else vnext = (double)sh->halo[par ^ 1][lane];
-            }
-            double a = 0.0, c = 1.0;
-#pragma unroll
-            for (int u = R - 1; u >= 0; --u) {
-                const int i = warp * R + u;
-                float rf = S.r[i][lane];
-                const float vf = S.v[i][lane];
-                const bool dn = S.d[i][lane] != 0;
-                if (p.has_pre) {
-                    rf = __double2float_rn((double)rf * inv_denom);
-                    rf = fminf(fmaxf(rf, p.clip_lo), p.clip_hi);
-                    const int64_t t = t0 + i;
-                    if (p.reward_out != nullptr && t >= 0 && col_ok) p.reward_out[t * p.ld_reward_out + col] = rf;
-                }
-                vreg[u] = vf;
+            if (REVERSE) {
+                float vnext_f = 0.f;
                 if (MODE == 0) {
-                    const double v = (double)vf;
-                    const double gnd = dn ? 0.0 : p.gamma;
-                    const double delta = fma(gnd, vnext, (double)rf) - v;
-                    const double cc = dn ? 0.0 : gl;
-                    a = fma(cc, a, delta);
-                    c = cc * c;
-                    vnext = v;
-                } else {
-                    const double cc = dn ? 0.0 : p.gamma;
-                    a = fma(cc, a, (double)rf);
-                    c = cc * c;
+                    if (warp == NWARPS - 1) vnext_f = (k == 0) ? halo_v : sh->halo[par ^ 1][lane];
+                    else vnext_f = S.v[i0 + R][lane];
                 }
-                A[u] = a;
-                C[u] = c;
+                ACC a = (ACC)0, c = (ACC)1;
+#pragma unroll
+                for (int u = R - 1; u >= 0; --u) {
+                    float rf = S.r[i0 + u][lane];
+                    const float vf = S.v[i0 + u][lane];
+                    const bool dn = S.d[i0 + u][lane] != 0;
+                    if (HAS_PRE) {
+                        rf = __double2float_rn((double)rf * inv_denom);
+                        rf = fminf(fmaxf(rf, clip_lo), clip_hi);
+                        O.o[PRE_SLOT][i0 + u][lane] = rf;
+                    }
+                    vreg[u] = vf;
+                    const ACC cc = dn ? (ACC)0 : (MODE == 0 ? gl : gamma);
+                    if (MODE == 0) {
+                        const ACC v = (ACC)vf;
+                        // done masks value[t+1] in float32 (one select) instead of masking gamma
+                        const ACC delta = fma(gamma, (ACC)(dn ? 0.f : vnext_f), (ACC)rf) - v;
+                        a = fma(cc, a, delta);
+                        vnext_f = vf;
+                    } else {
+                        a = fma(cc, a, (ACC)rf);
+                    }
+                    c = cc * c;
+                    A[u] = a;
+                    C[u] = c;
+                }
+                sh->aggA[par][warp][lane] = a;
+                sh->aggC[par][warp][lane] = c;
+                if (MODE == 0 && warp == 0) sh->halo[par][lane] = vreg[0];
+            } else {
+                // forward: x_t = r_t + g*~done[t-1]*x_{t-1}; S.d holds done rows t0-1 .. t0+TC-2
+                ACC a = (ACC)0, c = (ACC)1;
+#pragma unroll
+                for (int u = 0; u < R; ++u) {
+                    const float rf = S.r[i0 + u][lane];
+                    bool dn = S.d[i0 + u][lane] != 0;
+                    if (u == 0 && warp == 0 && k == 0) dn = first_prev_done;
+                    const ACC cc = dn ? (ACC)0 : gamma;
+                    a = fma(cc, a, (ACC)rf);
+                    c = cc * c;
+                    A[u] = a;
+                    C[u] = c;
+                }
+                sh->aggA[par][warp][lane] = a;
+                sh->aggC[par][warp][lane] = c;
             }
-            sh->aggA[par][warp][lane] = a;
-            sh->aggC[par][warp][lane] = c;
-            if (MODE == 0 && warp == 0) sh->halo[par][lane] = vreg[0];
-        } else {
-            // forward: x_t = r_t + g*~done[t-1]*x_{t-1}; S.d holds done rows t0-1 .. t0+TC-2
-            if (k == 0) carry = col_ok ? (double)p.prev_ret[col] : 0.0;
-            double a = 0.0, c = 1.0;
+
+            // outs[par] was last stored two tiles ago: make sure that TMA store has read it
+            if (threadIdx.x == 0) tma_store_wait_read<1>();
+            __syncthreads();  // stage fully read; aggregates visible; outs[par ^ 1] complete; outs[par] free
+
+            if (threadIdx.x == 0) {
+                if (iss_strip < n_strips) issue_one();   // refill the input stage just consumed
+                if (st_pending) store_tile(par ^ 1);     // previous tile's outputs -> global
+                st_pending = true;
+                st_c0 = strip * W;
+                st_t0 = (int)t0;
+            }
+
+            // carry entering this warp's rows + strip carry leaving the tile (all warps, redundantly)
+            ACC cin = carry;
+            {
+                ACC x = carry;
+                if (REVERSE) {
+#pragma unroll
+                    for (int w = NWARPS - 1; w >= 0; --w) {
+                        if (w == warp) cin = x;
+                        x = fma(sh->aggC[par][w][lane], x, sh->aggA[par][w][lane]);
+                    }
+                } else {
+#pragma unroll
+                    for (int w = 0; w < NWARPS; ++w) {
+                        if (w == warp) cin = x;
+                        x = fma(sh->aggC[par][w][lane], x, sh->aggA[par][w][lane]);
+                    }
+                }
+                carry = x;
+            }
+
+            // pass 2: finalise from registers into the output staging tile
+            const uint8_t *vp = (HAS_STATS && p.valid != nullptr) ? p.valid + (t0 + i0) * p.ld_valid + col : nullptr;
+            float s1 = 0.f, s2 = 0.f, piv = 0.f;  // float32 micro-accumulation of this tile's outputs
+            unsigned cnt = 0;
 #pragma unroll
             for (int u = 0; u < R; ++u) {
-                const int i = warp * R + u;
-                const float rf = S.r[i][lane];
-                bool dn = S.d[i][lane] != 0;
-                if (k == 0 && i == 0) dn = col_ok ? (p.prev_done[col] != 0) : false;
-                const double cc = dn ? 0.0 : p.gamma;
-                a = fma(cc, a, (double)rf);
-                c = cc * c;
-                A[u] = a;
-                C[u] = c;
+                const float x = to_f32(fma(C[u], cin, A[u]));
+                float y0;
+                if (MODE == 0) {
+                    y0 = x;
+                    O.o[0][i0 + u][lane] = x;
+                    O.o[1][i0 + u][lane] = __fadd_rn(x, vreg[u]);
+                } else if (MODE == 1) {
+                    y0 = __fsub_rn(x, vreg[u]);
+                    O.o[1][i0 + u][lane] = x;
+                    O.o[0][i0 + u][lane] = y0;
+                } else {
+                    y0 = x;
+                    O.o[0][i0 + u][lane] = x;
+                }
+                if (HAS_STATS) {
+                    const bool ok = col_ok && (uint64_t)(t0 + i0 + u) < (uint64_t)T;
+                    if (ok && (vp == nullptr || *vp != 0)) {
+                        if (cnt == 0) piv = y0;
+                        const float d = y0 - piv;
+                        s1 += d;
+                        s2 = fmaf(d, d, s2);
+                        ++cnt;
+                    }
+                    if (vp != nullptr) vp += p.ld_valid;
+                }
             }
-            sh->aggA[par][warp][lane] = a;
-            sh->aggC[par][warp][lane] = c;
-        }
+            fence_proxy_async_smem();  // staging-tile writes -> visible to the TMA store issued after the next barrier
+            if (HAS_STATS && cnt != 0) {
+                Moments m;
+                m.n = (double)cnt;
+                m.mean = (double)piv + (double)s1 / m.n;
+                m.m2 = fmax((double)s2 - (double)s1 * (double)s1 / m.n, 0.0);
+                acc = merge(acc, m);
+            }
 
-        __syncthreads();  // all smem reads of stage s done; aggregates visible
-
-        if (threadIdx.x == 0 && q + p.n_stages < Q) issue(q + p.n_stages);
-
-        // compose the carry entering this warp's rows, and the strip carry leaving the tile
-        double cin = carry;
-        if (REVERSE) {
-            double x = carry;
-#pragma unroll
-            for (int w = NWARPS - 1; w >= 0; --w) {
-                if (w == warp) cin = x;
-                x = fma(sh->aggC[par][w][lane], x, sh->aggA[par][w][lane]);
-            }
-            carry = x;
-        } else {
-            double x = carry;
-#pragma unroll
-            for (int w = 0; w < NWARPS; ++w) {
-                if (w == warp) cin = x;
-                x = fma(sh->aggC[par][w][lane], x, sh->aggA[par][w][lane]);
-            }
-            carry = x;
-        }
-
-        // pass 2: finalise from registers and store
-#pragma unroll
-        for (int u = 0; u < R; ++u) {
-            const int i = warp * R + u;
-            const int64_t t = t0 + i;
-            const bool ok = col_ok && t >= 0 && t < p.T;
-            const float x = __double2float_rn(fma(C[u], cin, A[u]));
-            if (!ok) continue;
-            float o0;
-            if (MODE == 0) {
-                o0 = x;
-                p.out0[t * p.ld0 + col] = x;
-                p.out1[t * p.ld1 + col] = __fadd_rn(x, vreg[u]);
-            } else if (MODE == 1) {
-                o0 = __fsub_rn(x, vreg[u]);
-                p.out1[t * p.ld1 + col] = x;
-                p.out0[t * p.ld0 + col] = o0;
-            } else {
-                o0 = x;
-                p.out0[t * p.ld0 + col] = x;
-            }
-            if (p.tail.moments_out != nullptr) {
-                if (p.valid == nullptr || p.valid[t * p.ld_valid + col] != 0) acc.add(o0);
-            }
+            par ^= 1;
+            if (++stage == n_stages) { stage = 0; phase ^= 1u; }
         }
     }
 
-    if (p.tail.moments_out != nullptr) moments_tail(acc.finish(), p.tail, red_scratch);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (st_pending) store_tile(par ^ 1);
+        tma_store_wait<0>();  // smem must stay alive (and global writes complete) before the CTA retires
+    }
+    if (HAS_STATS) moments_tail(acc, p.tail, red_scratch);
 }
 
 }  // namespace chunked
@@ -464,44 +537,119 @@ bool scan_chunked_supported(const float *reward, int64_t ld_r, const float *valu
     return tma_ok_u8(done, ld_d);
 }
 
-template <int MODE>
-static int launch_chunked(const float *reward, int64_t ld_r, const float *value, int64_t ld_v,
-                          const uint8_t *done, int64_t ld_d, chunked::Params p, cudaStream_t stream)
+template <int MODE, typename ACC, int R, bool HAS_PRE, bool HAS_STATS>
+static int launch_chunked_inst(const chunked::TensorMaps &tm, chunked::Params p, int sms, cudaStream_t stream)
 {
     using namespace chunked;
-    CUtensorMap tm_r, tm_v, tm_d;
-    int rc = make_tensor_map_2d(&tm_r, reward, 4, p.T, p.B, ld_r, TC, W);
-    if (rc) return rc;
-    if (MODE != 2) {
-        rc = make_tensor_map_2d(&tm_v, value, 4, p.T, p.B, ld_v, TC, W);
-        if (rc) return rc;
-    } else {
-        tm_v = tm_r;
-    }
-    rc = make_tensor_map_2d(&tm_d, done, 1, p.T, p.B, ld_d, TC, W);
-    if (rc) return rc;
-
-    const int sms = sm_count();
-    PLB_REQUIRE(sms > 0, PLB_ERR_UNSUPPORTED, "no CUDA device");
+    constexpr int TC = NWARPS * R;
+    constexpr int N_OUT = (MODE != 2 ? 2 : 1) + (HAS_PRE ? 1 : 0);
+    const size_t stage_bytes = sizeof(Stage<R>);
+    const size_t fixed_bytes = sizeof(Shared<ACC>) + 2 * sizeof(OutTile<R, N_OUT>);
     p.n_strips = (int)ceil_div(p.B, W);
     p.n_chunks = (int)ceil_div(p.T, TC);
-    int stages, ctas_per_sm;
-    if (p.n_strips <= sms) { stages = 8; ctas_per_sm = 1; }
-    else if (p.n_strips <= 2 * sms) { stages = 5; ctas_per_sm = 2; }
-    else { stages = 3; ctas_per_sm = 3; }
-    if (stages > p.n_chunks) stages = p.n_chunks < 1 ? 1 : p.n_chunks;
-    p.n_stages = stages;
-    const size_t smem = sizeof(Stage) * stages + sizeof(Shared);
-    int grid = p.n_strips < sms * ctas_per_sm ? p.n_strips : sms * ctas_per_sm;
-    auto kern = scan_chunked_kernel<MODE>;
-    static thread_local size_t configured = 0;
-    if (smem > configured) {
-        PLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(Stage) * MAX_STAGES + sizeof(Shared))));
-        configured = sizeof(Stage) * MAX_STAGES + sizeof(Shared);
+    // few strips: one CTA per SM with a deep ring; many strips: several CTAs per SM, shallow rings.
+    // 228 KB of shared memory per SM, 1 KB reserved per CTA, ~1 KB of static scratch per CTA.
+    int ctas_per_sm = p.n_strips <= sms ? 1 : (p.n_strips <= 2 * sms ? 2 : 3);
+    const size_t smem_cap = 227 * 1024 - 1024;
+    int stages = 0;
+    for (; ctas_per_sm >= 1; --ctas_per_sm) {
+        size_t budget = (size_t)(228 * 1024) / ctas_per_sm - 2048;
+        if (budget > smem_cap) budget = smem_cap;
+        stages = budget > fixed_bytes ? (int)((budget - fixed_bytes) / stage_bytes) : 0;
+        if (stages >= 2 || ctas_per_sm == 1) break;
     }
-    kern<<<grid, THREADS, smem, stream>>>(tm_r, tm_v, tm_d, p);
+    if (stages > MAX_STAGES) stages = MAX_STAGES;
+    if (stages > p.n_chunks) stages = p.n_chunks;
+    PLB_REQUIRE(stages >= 1, PLB_ERR_UNSUPPORTED, "chunked scan does not fit in shared memory");
+    p.n_stages = stages;
+    const size_t smem = stage_bytes * stages + fixed_bytes;
+    const int grid = p.n_strips < sms * ctas_per_sm ? p.n_strips : sms * ctas_per_sm;
+    auto kern = scan_chunked_kernel<MODE, ACC, R, HAS_PRE, HAS_STATS>;
+    static thread_local bool configured = false;
+    if (!configured) {
+        PLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
+        configured = true;
+    }
+    kern<<<grid, THREADS, smem, stream>>>(tm, p);
     PLB_LAUNCH_CHECK();
     return PLB_OK;
+}
+
+static int g_chunked_rows = 16;      // rows per warp per tile (8 or 16); tile = 8x that
+static int g_chunked_f32 = 0;        // 1: float32 affine maps (fast variant)
+
+struct ChunkedIO {
+    const float *reward; int64_t ld_r;
+    const float *value; int64_t ld_v;
+    const uint8_t *done; int64_t ld_d;
+    float *out0; int64_t ld0;
+    float *out1; int64_t ld1;
+    float *reward_out; int64_t ld_ro;
+};
+
+template <int MODE>
+static int launch_chunked(const ChunkedIO &io, chunked::Params p, bool has_pre, cudaStream_t stream)
+{
+    using namespace chunked;
+    const int sms = sm_count();
+    PLB_REQUIRE(sms > 0, PLB_ERR_UNSUPPORTED, "no CUDA device");
+    // deep 128-row tiles when there is one CTA per SM; 64-row tiles when several CTAs share an SM
+    const int R = (g_chunked_rows == 8 || p.T <= 64 || ceil_div(p.B, W) > sms) ? 8 : 16;
+    const int TC = NWARPS * R;
+    TensorMaps tm;
+    int rc = make_tensor_map_2d(&tm.r, io.reward, 4, p.T, p.B, io.ld_r, TC, W);
+    if (rc) return rc;
+    if (MODE != 2) {
+        rc = make_tensor_map_2d(&tm.v, io.value, 4, p.T, p.B, io.ld_v, TC, W);
+        if (rc) return rc;
+    } else {
+        tm.v = tm.r;
+    }
+    rc = make_tensor_map_2d(&tm.d, io.done, 1, p.T, p.B, io.ld_d, TC, W);
+    if (rc) return rc;
+    rc = make_tensor_map_2d(&tm.o0, io.out0, 4, p.T, p.B, io.ld0, TC, W);
+    if (rc) return rc;
+    if (MODE != 2) {
+        rc = make_tensor_map_2d(&tm.o1, io.out1, 4, p.T, p.B, io.ld1, TC, W);
+        if (rc) return rc;
+    } else {
+        tm.o1 = tm.o0;
+    }
+    if (has_pre) {
+        rc = make_tensor_map_2d(&tm.o2, io.reward_out, 4, p.T, p.B, io.ld_ro, TC, W);
+        if (rc) return rc;
+    } else {
+        tm.o2 = tm.o0;
+    }
+    tm.o0_rag = tm.o0; tm.o1_rag = tm.o1; tm.o2_rag = tm.o2;
+    const int ragged = (int)(p.T % TC);
+    if (MODE != 2 && ragged != 0) {
+        rc = make_tensor_map_2d(&tm.o0_rag, io.out0, 4, p.T, p.B, io.ld0, ragged, W);
+        if (rc) return rc;
+        rc = make_tensor_map_2d(&tm.o1_rag, io.out1, 4, p.T, p.B, io.ld1, ragged, W);
+        if (rc) return rc;
+        if (has_pre) {
+            rc = make_tensor_map_2d(&tm.o2_rag, io.reward_out, 4, p.T, p.B, io.ld_ro, ragged, W);
+            if (rc) return rc;
+        }
+    }
+    const bool stats = p.tail.moments_out != nullptr;
+#define PLB_DISPATCH(ACC_, R_)                                                                         \
+    do {                                                                                               \
+        if constexpr (MODE != 2) {                                                                     \
+            if (has_pre && stats) return launch_chunked_inst<MODE, ACC_, R_, true, true>(tm, p, sms, stream);   \
+            if (has_pre) return launch_chunked_inst<MODE, ACC_, R_, true, false>(tm, p, sms, stream);           \
+        }                                                                                              \
+        if (stats) return launch_chunked_inst<MODE, ACC_, R_, false, true>(tm, p, sms, stream);        \
+        return launch_chunked_inst<MODE, ACC_, R_, false, false>(tm, p, sms, stream);                  \
+    } while (0)
+    if (g_chunked_f32) {
+        if (R == 8) PLB_DISPATCH(float, 8);
+        PLB_DISPATCH(float, 16);
+    }
+    if (R == 8) PLB_DISPATCH(double, 8);
+    PLB_DISPATCH(double, 16);
+#undef PLB_DISPATCH
 }
 
 int scan_reverse(int mode, const float *reward, int64_t ld_r, const float *value, int64_t ld_v,
@@ -515,7 +663,10 @@ int scan_reverse(int mode, const float *reward, int64_t ld_r, const float *value
     PLB_REQUIRE(reward && value && done && boot && adv && ret, PLB_ERR_INVALID_ARGUMENT, "null pointer");
     PLB_REQUIRE(ld_r >= B && ld_d >= B && ld_v >= B * inner && ld_a >= B * inner && ld_t >= B * inner,
                 PLB_ERR_INVALID_ARGUMENT, "row stride smaller than row length");
-    const bool can_chunk = scan_chunked_supported(reward, ld_r, value, ld_v, done, ld_d, T, B, inner);
+    bool can_chunk = scan_chunked_supported(reward, ld_r, value, ld_v, done, ld_d, T, B, inner) &&
+                     tma_ok_f32(adv, ld_a) && tma_ok_f32(ret, ld_t);
+    if (fusion != nullptr && fusion->has_pre && fusion->reward_out != nullptr)
+        can_chunk = can_chunk && tma_ok_f32(fusion->reward_out, fusion->ld_reward_out);
     if (algo == PLB_ALGO_AUTO) {
         // the strict serial walk is memory-bound (and bit-exact) once there are enough columns
         algo = (can_chunk && B * inner < 32768) ? PLB_ALGO_CHUNKED : PLB_ALGO_SERIAL;
@@ -526,23 +677,26 @@ int scan_reverse(int mode, const float *reward, int64_t ld_r, const float *value
                     "chunked scan needs inner == 1, 16-byte aligned bases, ld %% 4 == 0 (float) and ld %% 16 == 0 (done)");
         chunked::Params p = {};
         p.boot = boot;
-        p.out0 = adv; p.ld0 = ld_a;
-        p.out1 = ret; p.ld1 = ld_t;
+        ChunkedIO io = {reward, ld_r, value, ld_v, done, ld_d, adv, ld_a, ret, ld_t, nullptr, 0};
         p.T = T; p.B = B;
         p.gamma = gamma; p.lambda = lambda;
         p.clip_lo = -INFINITY; p.clip_hi = INFINITY;
+        bool has_pre = false;
         if (fusion != nullptr) {
-            p.has_pre = fusion->has_pre;
+            has_pre = fusion->has_pre != 0;
             p.reward_var = fusion->reward_var;
             p.reward_eps = fusion->reward_eps;
             if (!(fusion->clip_lo != fusion->clip_lo)) p.clip_lo = (float)fusion->clip_lo;
             if (!(fusion->clip_hi != fusion->clip_hi)) p.clip_hi = (float)fusion->clip_hi;
-            p.reward_out = fusion->reward_out; p.ld_reward_out = fusion->ld_reward_out;
+            if (has_pre) {
+                PLB_REQUIRE(fusion->reward_out != nullptr, PLB_ERR_INVALID_ARGUMENT,
+                            "fused reward transform needs reward_out (it may alias reward)");
+                io.reward_out = fusion->reward_out; io.ld_ro = fusion->ld_reward_out;
+            }
             p.valid = fusion->valid; p.ld_valid = fusion->ld_valid;
             p.tail = fusion->tail;
         }
-        return mode == 0 ? launch_chunked<0>(reward, ld_r, value, ld_v, done, ld_d, p, stream)
-                         : launch_chunked<1>(reward, ld_r, value, ld_v, done, ld_d, p, stream);
+        return mode == 0 ? launch_chunked<0>(io, p, has_pre, stream) : launch_chunked<1>(io, p, has_pre, stream);
     }
     PLB_REQUIRE(algo == PLB_ALGO_SERIAL, PLB_ERR_INVALID_ARGUMENT, "unknown algo %d", algo);
     PLB_REQUIRE(fusion == nullptr, PLB_ERR_UNSUPPORTED, "fused transforms need the chunked scan");
@@ -567,7 +721,8 @@ int scan_forward(const float *reward, int64_t ld_r, const uint8_t *done, int64_t
     if (T == 0 || B == 0) return PLB_OK;
     PLB_REQUIRE(reward && done && prev_ret && prev_done && out, PLB_ERR_INVALID_ARGUMENT, "null pointer");
     PLB_REQUIRE(ld_r >= B && ld_d >= B && ld_o >= B, PLB_ERR_INVALID_ARGUMENT, "row stride smaller than row length");
-    const bool can_chunk = scan_chunked_supported(reward, ld_r, nullptr, 0, done, ld_d, T, B, 1);
+    const bool can_chunk = scan_chunked_supported(reward, ld_r, nullptr, 0, done, ld_d, T, B, 1) &&
+                           tma_ok_f32(out, ld_o);
     if (algo == PLB_ALGO_AUTO) {
         algo = (can_chunk && B < 32768) ? PLB_ALGO_CHUNKED : PLB_ALGO_SERIAL;
         if (fusion != nullptr && can_chunk) algo = PLB_ALGO_CHUNKED;
@@ -577,7 +732,7 @@ int scan_forward(const float *reward, int64_t ld_r, const uint8_t *done, int64_t
                     "chunked scan needs 16-byte aligned bases, ld %% 4 == 0 (float) and ld %% 16 == 0 (done)");
         chunked::Params p = {};
         p.prev_ret = prev_ret; p.prev_done = prev_done;
-        p.out0 = out; p.ld0 = ld_o;
+        ChunkedIO io = {reward, ld_r, nullptr, 0, done, ld_d, out, ld_o, nullptr, 0, nullptr, 0};
         p.T = T; p.B = B;
         p.gamma = gamma; p.lambda = 1.0;
         p.clip_lo = -INFINITY; p.clip_hi = INFINITY;
@@ -585,7 +740,7 @@ int scan_forward(const float *reward, int64_t ld_r, const uint8_t *done, int64_t
             p.valid = fusion->valid; p.ld_valid = fusion->ld_valid;
             p.tail = fusion->tail;
         }
-        return launch_chunked<2>(reward, ld_r, nullptr, 0, done, ld_d, p, stream);
+        return launch_chunked<2>(io, p, false, stream);
     }
     PLB_REQUIRE(algo == PLB_ALGO_SERIAL, PLB_ERR_INVALID_ARGUMENT, "unknown algo %d", algo);
     PLB_REQUIRE(fusion == nullptr, PLB_ERR_UNSUPPORTED, "fused statistics need the chunked scan");
@@ -599,6 +754,15 @@ int scan_forward(const float *reward, int64_t ld_r, const uint8_t *done, int64_t
 }  // namespace plb
 
 extern "C" {
+
+int plb_set_tuning(int key, int value)
+{
+    switch (key) {
+        case 0: plb::g_chunked_rows = value; return PLB_OK;
+        case 1: plb::g_chunked_f32 = value; return PLB_OK;
+        default: plb::set_error("unknown tuning key %d", key); return PLB_ERR_INVALID_ARGUMENT;
+    }
+}
 
 int plb_compute_gae_advantage_f32(const float *reward, int64_t ld_reward, const float *value, int64_t ld_value,
                                   const uint8_t *done, int64_t ld_done, const float *bootstrap_value,

@@ -17,7 +17,7 @@ def _make_device_tree(T, B, with_valid):
         "reward": DeviceArray((T, B), np.float32),
         "done": DeviceArray((T, B), np.bool_, padding=1),
         "agent_info": {"value": DeviceArray((T, B), np.float32)},
-        "bootstrap_value": torch.zeros(B, device="cuda"),
+        "bootstrap_value": DeviceArray((B,), np.float32),
         "advantage": DeviceArray((T, B), np.float32),
         "return_": DeviceArray((T, B), np.float32),
         "past_return": DeviceArray((T, B), np.float32, padding=1),

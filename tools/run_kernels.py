@@ -1,0 +1,100 @@
+"""Small driver that launches one hot-path kernel a few times (for ncu / timing sweeps).
+
+    python tools/run_kernels.py gae [--T 1024 --B 4096 --algo chunked --reps 5]
+    python tools/run_kernels.py norm_obs | gather | pipeline | moments
+"""
+import argparse
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from parllel_b200 import ArrayDict, BatchSpec  # noqa: E402
+from parllel_b200.replays import ReplayBuffer  # noqa: E402
+from parllel_b200.transforms import (EstimateAdvantage, NormalizeAdvantage,  # noqa: E402
+                                     NormalizeObservations, NormalizeRewards)
+
+
+def timed(fn, reps, flush=None):
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    for i in range(reps):
+        if flush is not None:
+            flush.zero_()
+        ev[i][0].record()
+        fn(i)
+        ev[i][1].record()
+    torch.cuda.synchronize()
+    return [a.elapsed_time(b) * 1e3 for a, b in ev]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("what")
+    ap.add_argument("--T", type=int, default=1024)
+    ap.add_argument("--B", type=int, default=4096)
+    ap.add_argument("--algo", default="chunked")
+    ap.add_argument("--lam", type=float, default=0.95)
+    ap.add_argument("--reps", type=int, default=20)
+    ap.add_argument("--n", type=int, default=16384)
+    ap.add_argument("--rows", type=int, default=0)
+    ap.add_argument("--f32", type=int, default=0)
+    args = ap.parse_args()
+    from parllel_b200 import _lib
+    if args.rows:
+        _lib.load().plb_set_tuning(0, args.rows)
+    _lib.load().plb_set_tuning(1, args.f32)
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(0)
+    flush = torch.empty(256 * 2**20, dtype=torch.uint8, device=dev)  # > L2
+    T, B = args.T, args.B
+    if args.what in ("gae", "normadv", "past"):
+        t = {"reward": torch.randn(T, B, device=dev), "done": torch.rand(T, B, device=dev) < 0.01,
+             "agent_info": {"value": torch.randn(T, B, device=dev)}, "bootstrap_value": torch.randn(B, device=dev),
+             "advantage": torch.empty(T, B, device=dev), "return_": torch.empty(T, B, device=dev),
+             "past_return": torch.empty(T, B, device=dev)}
+        tree = ArrayDict(t)
+        if args.what == "gae":
+            tf = EstimateAdvantage(0.99, args.lam, algo=args.algo)
+            nbytes = 17 * T * B
+        elif args.what == "normadv":
+            EstimateAdvantage(0.99, args.lam, algo=args.algo)(tree)
+            tf = NormalizeAdvantage(tree)
+            nbytes = 12 * T * B
+        else:
+            tf = NormalizeRewards(tree, 0.99, algo=args.algo)
+            nbytes = 17 * T * B
+        us = timed(lambda i: tf(tree), args.reps, flush)
+    elif args.what == "norm_obs":
+        B, shape = 1024, (3, 84, 84)
+        obs = torch.randn((4, B) + shape, device=dev) * 3 + 5
+        tf = NormalizeObservations({"observation": obs}, obs_shape=shape, initial_count=10000)
+        us = timed(lambda i: tf._step(obs[i % 4], None, dev), args.reps, flush)
+        nbytes = 8 * B * int(np.prod(shape))
+    elif args.what == "gather":
+        size_T, Bn = 62464, 16
+        ring = ArrayDict({
+            "observation": torch.randn(size_T + 2, Bn, 64, device=dev)[1:-1],
+            "next_observation": torch.randn(size_T, Bn, 64, device=dev),
+            "action": torch.randn(size_T, Bn, 8, device=dev),
+            "reward": torch.randn(size_T, Bn, device=dev),
+            "terminated": torch.rand(size_T, Bn, device=dev) < 0.01})
+        rb = ReplayBuffer(ring, BatchSpec(128, Bn), size_T=size_T, replay_batch_size=args.n, oldest_n_samples_invalid=1)
+        rb._full, rb._cursor = True, 384
+        rb.seed(0)
+        idx = [tuple(torch.from_numpy(a).to(dev) for a in rb.sample_indices()) for _ in range(4)]
+        us = timed(lambda i: rb.gather(*idx[i % 4]), args.reps, flush)
+        nbytes = 1114 * args.n
+    else:
+        raise SystemExit(f"unknown kernel {args.what}")
+    us = sorted(us)
+    med = us[len(us) // 2]
+    print(f"{args.what} T={T} B={B} algo={args.algo} rows={args.rows} f32={args.f32}: median {med:.2f} us  min {us[0]:.2f} us  "
+          f"-> {nbytes / med / 1e3:.1f} GB/s (median), {nbytes / us[0] / 1e3:.1f} GB/s (best)  [{nbytes} algorithmic bytes]")
+
+
+if __name__ == "__main__":
+    main()
