@@ -67,9 +67,9 @@ PLB_API const char *plb_last_error(void);
 /* Number of SMs of the current device (grid sizing); <0 on error. */
 PLB_API int plb_sm_count(void);
 /* Tuning / diagnostics knobs (process-wide; used by tools/ and the tests, not by the transforms).
- *   key 0: rows per warp per tile of the chunked scan (8 or 16; default 16 when one CTA per SM)
+ *   key 0: tile geometry of the chunked scan: 0 auto, 1 = 8 warps x 8 rows, 2 = 8 x 16, 3 = 16 x 8
  *   key 1: 1 = float32 affine maps in the chunked scan (default 0 = float64) */
-#define PLB_TUNE_CHUNK_ROWS 0
+#define PLB_TUNE_CHUNK_GEOMETRY 0
 #define PLB_TUNE_CHUNK_F32 1
 PLB_API int plb_set_tuning(int key, int value);
 
@@ -214,6 +214,51 @@ PLB_API int plb_gather_tree(
     const plb_gather_leaf *leaves, int32_t n_leaves,
     const int64_t *t_idx, const int64_t *b_idx, int64_t n,
     plb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * Fused batch-transform chain        parllel/samplers/basic.py:124-125 (`for transform in
+ * batch_transforms: sample_tree = transform(sample_tree)`) specialised to the chain the examples
+ * build (examples/cartpole/train_ppo.py:101-121):
+ *   NormalizeRewards -> ClipRewards -> EstimateAdvantage -> NormalizeAdvantage
+ * Each stage can be switched off.  Results equal the four separate calls (same kernels' maths);
+ * the reward rescale/clip is folded into the advantage scan's load path and the advantage
+ * moments into its store path.  `phases` selects which part to enqueue so that a multi-GPU host
+ * can merge `return_moments` (after A) and `advantage_moments` (after B) across ranks with
+ * plb_merge_moments_f64 before the next phase; single-GPU callers pass PLB_PHASE_ALL.
+ * ---------------------------------------------------------------------------------- */
+#define PLB_PHASE_A 1 /* past-return scan + moments of past_return            */
+#define PLB_PHASE_B 2 /* update running stats; advantage scan (+scale/clip, +advantage moments) */
+#define PLB_PHASE_C 4 /* normalise advantage                                  */
+#define PLB_PHASE_ALL 7
+
+typedef struct {
+    int64_t T, B;
+    /* leaves ([T, B] views, row strides in elements) */
+    float *reward; int64_t ld_reward;                /* in/out */
+    const float *value; int64_t ld_value;
+    const uint8_t *done; int64_t ld_done;
+    const float *bootstrap_value;                    /* [B] */
+    float *advantage; int64_t ld_advantage;          /* out */
+    float *return_; int64_t ld_return;               /* out */
+    float *past_return; int64_t ld_past_return;      /* out (NormalizeRewards) */
+    const float *previous_return;                    /* [B]  past_return[-1] */
+    const uint8_t *previous_done;                    /* [B]  done[-1]        */
+    const uint8_t *valid; int64_t ld_valid;          /* optional mask for the statistics, or NULL */
+    /* stages */
+    int32_t normalize_rewards, clip_rewards, estimate_advantage, normalize_advantage;
+    double discount, gae_lambda;
+    double clip_lo, clip_hi;                         /* NaN = no bound */
+    double eps_reward, eps_advantage;                /* 1e-6 in the reference */
+    /* device-resident state / scratch */
+    double *return_mean, *return_var, *return_count; /* RunningMeanStd(shape=()) of NormalizeRewards */
+    double *return_moments;                          /* [3] batch moments of past_return   */
+    double *advantage_moments;                       /* [3] batch moments of advantage     */
+    int32_t moments_flags;                           /* PLB_MOMENTS_F32_FLOW or 0 */
+    void *workspace; size_t workspace_bytes;
+} plb_batch_pipeline;
+
+PLB_API size_t plb_batch_pipeline_workspace_bytes(void);
+PLB_API int plb_batch_pipeline_f32(const plb_batch_pipeline *desc, int phases, plb_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -48,6 +48,7 @@ class Staging:
 
     def __init__(self, device: torch.device | None = None) -> None:
         self.device = device
+        self.staged = False  # True once any host leaf had to be copied to the device
         self._writebacks: list[tuple[torch.Tensor, torch.Tensor]] = []
 
     def _adopt_device(self, t: torch.Tensor) -> None:
@@ -66,6 +67,7 @@ class Staging:
             self.device = default_device()
         # zero-copy torch view of the caller's host buffer (pinned memory is recognised by torch
         # through cudaPointerGetAttributes, in which case the copies below are direct DMA)
+        self.staged = True
         host = leaf.detach() if isinstance(leaf, torch.Tensor) else torch.from_numpy(np.asarray(leaf))
         dev = torch.empty(host.shape, dtype=host.dtype, device=self.device)
         dev.copy_(host, non_blocking=True)

@@ -27,6 +27,33 @@ class GatherLeaf(ctypes.Structure):
                 ("stride_t_bytes", c_int64), ("stride_b_bytes", c_int64)]
 
 
+class BatchPipeline(ctypes.Structure):
+    """``plb_batch_pipeline`` (include/parllel_b200.h)."""
+    _fields_ = [
+        ("T", c_int64), ("B", c_int64),
+        ("reward", c_void_p), ("ld_reward", c_int64),
+        ("value", c_void_p), ("ld_value", c_int64),
+        ("done", c_void_p), ("ld_done", c_int64),
+        ("bootstrap_value", c_void_p),
+        ("advantage", c_void_p), ("ld_advantage", c_int64),
+        ("return_", c_void_p), ("ld_return", c_int64),
+        ("past_return", c_void_p), ("ld_past_return", c_int64),
+        ("previous_return", c_void_p), ("previous_done", c_void_p),
+        ("valid", c_void_p), ("ld_valid", c_int64),
+        ("normalize_rewards", c_int32), ("clip_rewards", c_int32),
+        ("estimate_advantage", c_int32), ("normalize_advantage", c_int32),
+        ("discount", c_double), ("gae_lambda", c_double),
+        ("clip_lo", c_double), ("clip_hi", c_double),
+        ("eps_reward", c_double), ("eps_advantage", c_double),
+        ("return_mean", c_void_p), ("return_var", c_void_p), ("return_count", c_void_p),
+        ("return_moments", c_void_p), ("advantage_moments", c_void_p),
+        ("moments_flags", c_int32),
+        ("workspace", c_void_p), ("workspace_bytes", c_size_t),
+    ]
+
+
+PHASE_A, PHASE_B, PHASE_C, PHASE_ALL = 1, 2, 4, 7
+
 _SIGNATURES = {
     "plb_version": ([], c_int),
     "plb_last_error": ([], ctypes.c_char_p),
@@ -63,12 +90,12 @@ _SIGNATURES = {
          c_void_p, c_size_t, c_void_p], c_int),
     "plb_gather_tree": (
         [ctypes.POINTER(GatherLeaf), c_int32, c_void_p, c_void_p, c_int64, c_void_p], c_int),
+    "plb_batch_pipeline_workspace_bytes": ([], c_size_t),
+    "plb_batch_pipeline_f32": ([ctypes.POINTER(BatchPipeline), c_int, c_void_p], c_int),
 }
 
 # entry points added after the first release are bound when present (see include/parllel_b200.h)
 _OPTIONAL = {
-    "plb_batch_pipeline_workspace_bytes": ([], c_size_t),
-    "plb_batch_pipeline_f32": ([c_void_p, c_void_p], c_int),
     "plb_replay_sample_indices": None,
 }
 

@@ -15,6 +15,7 @@ template <bool VEC4, class F>
 __global__ void __launch_bounds__(256)
 elementwise_kernel(float *__restrict__ x, int64_t ld_x, int64_t rows, int64_t cols, F f)
 {
+    f.prepare();  // per-launch constants -> registers (the stores to x could alias them otherwise)
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
     if (VEC4) {
@@ -85,11 +86,13 @@ struct ScaleClipOp {
     const double *var;
     double eps;
     float lo, hi;
+    double denom;
+    __device__ __forceinline__ void prepare() { denom = (var != nullptr) ? sqrt(__dadd_rn(*var, eps)) : 1.0; }
     __device__ __forceinline__ float operator()(float x, int64_t) const
     {
         if (var != nullptr) {
             // one float64 division per element, like the reference (norm_rewards.py:114)
-            x = __double2float_rn(__ddiv_rn((double)x, sqrt(__dadd_rn(*var, eps))));
+            x = __double2float_rn(__ddiv_rn((double)x, denom));
         }
         return fminf(fmaxf(x, lo), hi);
     }
@@ -100,9 +103,16 @@ struct NormAdvOp {
     const double *moments;  // [inner][3]
     int64_t inner;
     float eps;
+    float mean0, denom0;    // single-agent case, hoisted
+    __device__ __forceinline__ void prepare()
+    {
+        mean0 = __double2float_rn(moments[1]);
+        denom0 = __fadd_rn(__double2float_rn(sqrt(moments[2] / moments[0])), eps);
+    }
     __device__ __forceinline__ float operator()(float x, int64_t col) const
     {
-        const double *m = moments + 3 * (inner == 1 ? 0 : col % inner);
+        if (inner == 1) return __fdiv_rn(__fsub_rn(x, mean0), denom0);
+        const double *m = moments + 3 * (col % inner);
         const float mean = __double2float_rn(m[1]);
         const float stdv = __double2float_rn(sqrt(m[2] / m[0]));
         return __fdiv_rn(__fsub_rn(x, mean), __fadd_rn(stdv, eps));
@@ -113,6 +123,7 @@ struct NormAdvOp {
 struct NormColsOp {
     const double *mean, *var;
     double eps;
+    __device__ __forceinline__ void prepare() {}
     __device__ __forceinline__ float operator()(float x, int64_t col) const
     {
         return __double2float_rn(__ddiv_rn(__dsub_rn((double)x, mean[col]), sqrt(__dadd_rn(var[col], eps))));

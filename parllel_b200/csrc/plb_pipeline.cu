@@ -1,0 +1,145 @@
+// plb_pipeline.cu -- the fused batch-transform chain of the samplers (samplers/basic.py:124-125):
+//
+//     NormalizeRewards -> ClipRewards -> EstimateAdvantage -> NormalizeAdvantage
+//     (norm_rewards.py:86-116, clip_rewards.py:31-38, advantage.py:91-106, norm_advantage.py:30-56)
+//
+// One C call enqueues the whole chain.  Compared with calling the four transforms one by one,
+// the reward rescale + clip is folded into the load path of the advantage scan (the transformed
+// reward is written back once), and the moments NormalizeAdvantage needs are accumulated in the
+// store path of the same scan, so the batch is streamed 3 times instead of 6:
+//
+//   phase A  forward past-return scan  + fused moments of past_return      (read 5 B, write 4 B /tr)
+//   phase B  update running statistics; advantage scan with fused reward
+//            scale/clip on load and advantage moments on store             (read 9 B, write 12 B /tr)
+//   phase C  normalise advantage                                           (read 4 B, write 4 B /tr)
+//
+// The phases are separately selectable so a multi-GPU host can all-gather + merge the moments
+// (plb_merge_moments_f64) between them.  Any stage can be switched off; shapes the TMA scan cannot
+// describe fall back to the unfused kernels with identical results.
+#include <math.h>
+
+#include "plb_common.cuh"
+#include "plb_scan_shared.cuh"
+
+namespace plb {
+
+static bool is_nan(double x) { return x != x; }
+
+static int run_pipeline(const plb_batch_pipeline *d, int phases, cudaStream_t stream)
+{
+    PLB_REQUIRE(d != nullptr, PLB_ERR_INVALID_ARGUMENT, "null descriptor");
+    PLB_REQUIRE(d->T >= 0 && d->B >= 0, PLB_ERR_INVALID_ARGUMENT, "negative extent");
+    if (d->T == 0 || d->B == 0) return PLB_OK;
+    const int64_t T = d->T, B = d->B;
+    const bool norm_rew = d->normalize_rewards != 0;
+    const bool clip = d->clip_rewards != 0;
+    const bool est_adv = d->estimate_advantage != 0;
+    const bool norm_adv = d->normalize_advantage != 0;
+    PLB_REQUIRE(d->reward != nullptr || !(norm_rew || clip || est_adv), PLB_ERR_INVALID_ARGUMENT, "reward is null");
+    const size_t ws_need = 2 * MOMENTS_WS_BYTES;
+    PLB_REQUIRE(d->workspace != nullptr && d->workspace_bytes >= ws_need, PLB_ERR_WORKSPACE,
+                "pipeline needs %zu workspace bytes, got %zu", ws_need, d->workspace_bytes);
+    unsigned char *ws = reinterpret_cast<unsigned char *>(d->workspace);
+    void *ws_a = ws, *ws_b = ws + MOMENTS_WS_BYTES;
+    int rc;
+
+    // ---------------------------------------------------------------- phase A
+    if ((phases & PLB_PHASE_A) && norm_rew) {
+        PLB_REQUIRE(d->done && d->past_return && d->previous_return && d->previous_done && d->return_moments,
+                    PLB_ERR_INVALID_ARGUMENT, "NormalizeRewards stage: missing leaf");
+        ScanFusion f = {};
+        f.valid = d->valid; f.ld_valid = d->ld_valid;
+        f.tail = make_tail(d->return_moments, ws_a);
+        rc = scan_forward(d->reward, d->ld_reward, d->done, d->ld_done, d->previous_return, d->previous_done,
+                          d->past_return, d->ld_past_return, T, B, d->discount, PLB_ALGO_CHUNKED, &f, stream);
+        if (rc == PLB_ERR_UNSUPPORTED) {  // shape TMA cannot describe: serial scan + separate moments
+            rc = scan_forward(d->reward, d->ld_reward, d->done, d->ld_done, d->previous_return, d->previous_done,
+                              d->past_return, d->ld_past_return, T, B, d->discount, PLB_ALGO_SERIAL, nullptr, stream);
+            if (rc) return rc;
+            rc = plb_batch_moments_f32(d->past_return, d->ld_past_return, T, B, d->valid, d->ld_valid,
+                                       d->return_moments, ws_a, MOMENTS_WS_BYTES, stream);
+        }
+        if (rc) return rc;
+    }
+
+    // ---------------------------------------------------------------- phase B
+    if (phases & PLB_PHASE_B) {
+        if (norm_rew) {
+            PLB_REQUIRE(d->return_mean && d->return_var && d->return_count, PLB_ERR_INVALID_ARGUMENT,
+                        "NormalizeRewards stage: missing running statistics");
+            rc = plb_update_from_moments_f64(d->return_moments, d->return_moments + 1, d->return_moments + 2,
+                                             d->return_mean, d->return_var, d->return_count, 1,
+                                             d->moments_flags, stream);
+            if (rc) return rc;
+        }
+        const double lo = clip ? d->clip_lo : NAN, hi = clip ? d->clip_hi : NAN;
+        const bool has_pre = norm_rew || (clip && !(is_nan(lo) && is_nan(hi)));
+        if (est_adv) {
+            PLB_REQUIRE(d->value && d->done && d->bootstrap_value && d->advantage && d->return_,
+                        PLB_ERR_INVALID_ARGUMENT, "EstimateAdvantage stage: missing leaf");
+            PLB_REQUIRE(!norm_adv || d->advantage_moments, PLB_ERR_INVALID_ARGUMENT, "advantage_moments is null");
+            ScanFusion f = {};
+            f.has_pre = has_pre ? 1 : 0;
+            f.reward_var = norm_rew ? d->return_var : nullptr;
+            f.reward_eps = d->eps_reward;
+            f.clip_lo = lo; f.clip_hi = hi;
+            f.reward_out = d->reward; f.ld_reward_out = d->ld_reward;
+            if (norm_adv) {
+                f.valid = d->valid; f.ld_valid = d->ld_valid;
+                f.tail = make_tail(d->advantage_moments, ws_b);
+            }
+            const int mode = (d->gae_lambda == 1.0) ? 1 : 0;
+            rc = scan_reverse(mode, d->reward, d->ld_reward, d->value, d->ld_value, d->done, d->ld_done,
+                              d->bootstrap_value, d->advantage, d->ld_advantage, d->return_, d->ld_return,
+                              T, B, 1, d->discount, d->gae_lambda, PLB_ALGO_CHUNKED,
+                              (has_pre || norm_adv) ? &f : nullptr, stream);
+            if (rc == PLB_ERR_UNSUPPORTED) {  // unfused fallback, same results
+                if (has_pre) {
+                    rc = plb_scale_clip_f32(d->reward, d->ld_reward, T, B, f.reward_var, d->eps_reward, lo, hi, stream);
+                    if (rc) return rc;
+                }
+                rc = scan_reverse(mode, d->reward, d->ld_reward, d->value, d->ld_value, d->done, d->ld_done,
+                                  d->bootstrap_value, d->advantage, d->ld_advantage, d->return_, d->ld_return,
+                                  T, B, 1, d->discount, d->gae_lambda, PLB_ALGO_SERIAL, nullptr, stream);
+                if (rc) return rc;
+                if (norm_adv)
+                    rc = plb_batch_moments_f32(d->advantage, d->ld_advantage, T, B, d->valid, d->ld_valid,
+                                               d->advantage_moments, ws_b, MOMENTS_WS_BYTES, stream);
+            }
+            if (rc) return rc;
+        } else {
+            if (has_pre) {
+                rc = plb_scale_clip_f32(d->reward, d->ld_reward, T, B, norm_rew ? d->return_var : nullptr,
+                                        d->eps_reward, lo, hi, stream);
+                if (rc) return rc;
+            }
+            if (norm_adv) {
+                PLB_REQUIRE(d->advantage && d->advantage_moments, PLB_ERR_INVALID_ARGUMENT, "advantage is null");
+                rc = plb_batch_moments_f32(d->advantage, d->ld_advantage, T, B, d->valid, d->ld_valid,
+                                           d->advantage_moments, ws_b, MOMENTS_WS_BYTES, stream);
+                if (rc) return rc;
+            }
+        }
+    }
+
+    // ---------------------------------------------------------------- phase C
+    if ((phases & PLB_PHASE_C) && norm_adv) {
+        rc = plb_normalize_advantage_f32(d->advantage, d->ld_advantage, T, B, 1, d->advantage_moments,
+                                         d->eps_advantage, stream);
+        if (rc) return rc;
+    }
+    return PLB_OK;
+}
+
+}  // namespace plb
+
+extern "C" {
+
+size_t plb_batch_pipeline_workspace_bytes(void) { return 2 * plb::MOMENTS_WS_BYTES; }
+
+int plb_batch_pipeline_f32(const plb_batch_pipeline *desc, int phases, plb_stream_t stream)
+{
+    return plb::run_pipeline(desc, phases, (cudaStream_t)stream);
+}
+
+}  // extern "C"

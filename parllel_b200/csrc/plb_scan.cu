@@ -173,28 +173,28 @@ scan_forward_serial_kernel(const float *__restrict__ reward, int64_t ld_r,
 namespace chunked {
 
 constexpr int W = 32;        // columns per strip (one lane per column)
-constexpr int NWARPS = 8;    // warps per CTA; warp w owns rows [w*R, (w+1)*R) of a tile
-constexpr int THREADS = NWARPS * 32;
 constexpr int MAX_STAGES = 12;
 
-// one input pipeline stage: three TMA boxes of TC = NWARPS*R rows x 32 columns
-template <int R>
+// one input pipeline stage: three TMA boxes of TC rows x 32 columns
+// (TC = NW warps x R rows; warp w owns rows [w*R, (w+1)*R) of a tile)
+template <int TC>
 struct __align__(128) Stage {
-    float r[NWARPS * R][W];
-    float v[NWARPS * R][W];
-    uint8_t d[NWARPS * R][W];
+    float r[TC][W];
+    float v[TC][W];
+    uint8_t d[TC][W];
 };
 
 // one output staging buffer (TMA-stored to global; the TMA clips rows/columns outside the tensor)
-template <int R, int N_OUT>
+template <int TC, int N_OUT>
 struct __align__(128) OutTile {
-    float o[N_OUT][NWARPS * R][W];
+    float o[N_OUT][TC][W];
 };
 
-template <typename ACC>
+template <typename ACC, int NW>
 struct Shared {
-    ACC aggA[2][NWARPS][W];
-    ACC aggC[2][NWARPS][W];
+    ACC aggA[2][NW][W];
+    ACC aggC[2][NW][W];
+    ACC carry[2][W];
     float halo[2][W];
     unsigned long long full[MAX_STAGES];
 };
@@ -232,18 +232,19 @@ __device__ __forceinline__ float to_f32(float x) { return x; }
 // ACC: arithmetic type of the affine maps (double = default; float = fast variant).
 // Output slots: MODE 0: o0 = advantage, o1 = return_; MODE 1: same; MODE 2: o0 = past_return;
 //               HAS_PRE adds the transformed reward as the last slot.
-template <int MODE, typename ACC, int R, bool HAS_PRE, bool HAS_STATS>
-__global__ void __launch_bounds__(THREADS)
+template <int MODE, typename ACC, int NW, int R, bool HAS_PRE, bool HAS_STATS>
+__global__ void __launch_bounds__(NW * 32)
 scan_chunked_kernel(const __grid_constant__ TensorMaps tm, const Params p)
 {
-    constexpr int TC = NWARPS * R;
+    constexpr int TC = NW * R;
+    constexpr int NWARPS = NW;
     constexpr bool REVERSE = (MODE != 2);
     constexpr int N_OUT = (REVERSE ? 2 : 1) + (HAS_PRE ? 1 : 0);
     constexpr int PRE_SLOT = N_OUT - 1;
     constexpr uint32_t TX_BYTES = REVERSE ? (sizeof(float) * TC * W * 2 + TC * W) : (sizeof(float) * TC * W + TC * W);
-    using StageT = Stage<R>;
-    using OutT = OutTile<R, N_OUT>;
-    using SharedT = Shared<ACC>;
+    using StageT = Stage<TC>;
+    using OutT = OutTile<TC, N_OUT>;
+    using SharedT = Shared<ACC, NW>;
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     StageT *stages = reinterpret_cast<StageT *>(smem_raw);
@@ -257,7 +258,7 @@ scan_chunked_kernel(const __grid_constant__ TensorMaps tm, const Params p)
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < n_stages; ++s) mbar_init(&sh->full[s], 1);
-        fence_mbar_init();
+        fence_proxy_async_smem();  // barrier inits (generic proxy) -> visible to the TMA (async proxy)
     }
     __syncthreads();
 
@@ -324,10 +325,10 @@ scan_chunked_kernel(const __grid_constant__ TensorMaps tm, const Params p)
     for (int strip = blockIdx.x; strip < n_strips; strip += gridDim.x) {
         const int64_t col = (int64_t)strip * W + lane;
         const bool col_ok = col < p.B;
-        ACC carry;  // scan value just outside the current tile, per column
-        if (MODE == 0) carry = (ACC)0;
-        else if (MODE == 1) carry = col_ok ? (ACC)p.boot[col] : (ACC)0;
-        else carry = col_ok ? (ACC)p.prev_ret[col] : (ACC)0;
+        ACC carry0;  // scan value entering the first tile of the strip, per column
+        if (MODE == 0) carry0 = (ACC)0;
+        else if (MODE == 1) carry0 = col_ok ? (ACC)p.boot[col] : (ACC)0;
+        else carry0 = col_ok ? (ACC)p.prev_ret[col] : (ACC)0;
         float halo_v = 0.f;  // GAE: value[t+1] for the last row of the first tile = bootstrap value
         if (MODE == 0 && warp == NWARPS - 1) halo_v = col_ok ? p.boot[col] : 0.f;
         bool first_prev_done = false;
@@ -408,24 +409,17 @@ scan_chunked_kernel(const __grid_constant__ TensorMaps tm, const Params p)
                 st_t0 = (int)t0;
             }
 
-            // carry entering this warp's rows + strip carry leaving the tile (all warps, redundantly)
-            ACC cin = carry;
-            {
-                ACC x = carry;
-                if (REVERSE) {
-#pragma unroll
-                    for (int w = NWARPS - 1; w >= 0; --w) {
-                        if (w == warp) cin = x;
-                        x = fma(sh->aggC[par][w][lane], x, sh->aggA[par][w][lane]);
-                    }
-                } else {
-#pragma unroll
-                    for (int w = 0; w < NWARPS; ++w) {
-                        if (w == warp) cin = x;
-                        x = fma(sh->aggC[par][w][lane], x, sh->aggA[par][w][lane]);
-                    }
-                }
-                carry = x;
+            // Carry entering this warp's rows: the strip carry of the tile (published through smem by
+            // the warp that finished the previous tile's chain) composed with the aggregates of the
+            // warps that precede this one in scan order.  The last warp of the chain publishes the
+            // carry for the next tile.
+            ACC cin = (k == 0) ? carry0 : sh->carry[par ^ 1][lane];
+            if (REVERSE) {
+                for (int w = NWARPS - 1; w > warp; --w) cin = fma(sh->aggC[par][w][lane], cin, sh->aggA[par][w][lane]);
+                if (warp == 0) sh->carry[par][lane] = fma(C[0], cin, A[0]);
+            } else {
+                for (int w = 0; w < warp; ++w) cin = fma(sh->aggC[par][w][lane], cin, sh->aggA[par][w][lane]);
+                if (warp == NWARPS - 1) sh->carry[par][lane] = fma(C[R - 1], cin, A[R - 1]);
             }
 
             // pass 2: finalise from registers into the output staging tile
@@ -537,19 +531,20 @@ bool scan_chunked_supported(const float *reward, int64_t ld_r, const float *valu
     return tma_ok_u8(done, ld_d);
 }
 
-template <int MODE, typename ACC, int R, bool HAS_PRE, bool HAS_STATS>
+template <int MODE, typename ACC, int NW, int R, bool HAS_PRE, bool HAS_STATS>
 static int launch_chunked_inst(const chunked::TensorMaps &tm, chunked::Params p, int sms, cudaStream_t stream)
 {
     using namespace chunked;
-    constexpr int TC = NWARPS * R;
+    constexpr int TC = NW * R;
     constexpr int N_OUT = (MODE != 2 ? 2 : 1) + (HAS_PRE ? 1 : 0);
-    const size_t stage_bytes = sizeof(Stage<R>);
-    const size_t fixed_bytes = sizeof(Shared<ACC>) + 2 * sizeof(OutTile<R, N_OUT>);
+    const size_t stage_bytes = sizeof(Stage<TC>);
+    const size_t fixed_bytes = sizeof(Shared<ACC, NW>) + 2 * sizeof(OutTile<TC, N_OUT>);
     p.n_strips = (int)ceil_div(p.B, W);
     p.n_chunks = (int)ceil_div(p.T, TC);
     // few strips: one CTA per SM with a deep ring; many strips: several CTAs per SM, shallow rings.
     // 228 KB of shared memory per SM, 1 KB reserved per CTA, ~1 KB of static scratch per CTA.
     int ctas_per_sm = p.n_strips <= sms ? 1 : (p.n_strips <= 2 * sms ? 2 : 3);
+    if (NW > 8) ctas_per_sm = 1;
     const size_t smem_cap = 227 * 1024 - 1024;
     int stages = 0;
     for (; ctas_per_sm >= 1; --ctas_per_sm) {
@@ -564,18 +559,19 @@ static int launch_chunked_inst(const chunked::TensorMaps &tm, chunked::Params p,
     p.n_stages = stages;
     const size_t smem = stage_bytes * stages + fixed_bytes;
     const int grid = p.n_strips < sms * ctas_per_sm ? p.n_strips : sms * ctas_per_sm;
-    auto kern = scan_chunked_kernel<MODE, ACC, R, HAS_PRE, HAS_STATS>;
+    auto kern = scan_chunked_kernel<MODE, ACC, NW, R, HAS_PRE, HAS_STATS>;
     static thread_local bool configured = false;
     if (!configured) {
         PLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
         configured = true;
     }
-    kern<<<grid, THREADS, smem, stream>>>(tm, p);
+    kern<<<grid, NW * 32, smem, stream>>>(tm, p);
     PLB_LAUNCH_CHECK();
     return PLB_OK;
 }
 
-static int g_chunked_rows = 16;      // rows per warp per tile (8 or 16); tile = 8x that
+// tile geometry: 0 = auto, 1 = 8 warps x 8 rows (64-row tiles), 2 = 8 warps x 16 rows, 3 = 16 warps x 8 rows
+static int g_chunked_geom = 0;
 static int g_chunked_f32 = 0;        // 1: float32 affine maps (fast variant)
 
 struct ChunkedIO {
@@ -593,9 +589,12 @@ static int launch_chunked(const ChunkedIO &io, chunked::Params p, bool has_pre, 
     using namespace chunked;
     const int sms = sm_count();
     PLB_REQUIRE(sms > 0, PLB_ERR_UNSUPPORTED, "no CUDA device");
-    // deep 128-row tiles when there is one CTA per SM; 64-row tiles when several CTAs share an SM
-    const int R = (g_chunked_rows == 8 || p.T <= 64 || ceil_div(p.B, W) > sms) ? 8 : 16;
-    const int TC = NWARPS * R;
+    // one CTA per SM (few strips): 16 warps x 8 rows = 128-row tiles, all the latency hiding one CTA
+    // can get; several CTAs per SM (many strips): 8 warps x 8 rows = 64-row tiles.
+    int geom = g_chunked_geom;
+    if (geom == 0) geom = (p.T <= 64 || ceil_div(p.B, W) > sms) ? 1 : 3;
+    if (p.T <= 64) geom = 1;
+    const int TC = geom == 1 ? 64 : 128;
     TensorMaps tm;
     int rc = make_tensor_map_2d(&tm.r, io.reward, 4, p.T, p.B, io.ld_r, TC, W);
     if (rc) return rc;
@@ -634,21 +633,23 @@ static int launch_chunked(const ChunkedIO &io, chunked::Params p, bool has_pre, 
         }
     }
     const bool stats = p.tail.moments_out != nullptr;
-#define PLB_DISPATCH(ACC_, R_)                                                                         \
-    do {                                                                                               \
-        if constexpr (MODE != 2) {                                                                     \
-            if (has_pre && stats) return launch_chunked_inst<MODE, ACC_, R_, true, true>(tm, p, sms, stream);   \
-            if (has_pre) return launch_chunked_inst<MODE, ACC_, R_, true, false>(tm, p, sms, stream);           \
-        }                                                                                              \
-        if (stats) return launch_chunked_inst<MODE, ACC_, R_, false, true>(tm, p, sms, stream);        \
-        return launch_chunked_inst<MODE, ACC_, R_, false, false>(tm, p, sms, stream);                  \
+#define PLB_DISPATCH(ACC_, NW_, R_)                                                                          \
+    do {                                                                                                     \
+        if constexpr (MODE != 2) {                                                                           \
+            if (has_pre && stats) return launch_chunked_inst<MODE, ACC_, NW_, R_, true, true>(tm, p, sms, stream);   \
+            if (has_pre) return launch_chunked_inst<MODE, ACC_, NW_, R_, true, false>(tm, p, sms, stream);           \
+        }                                                                                                    \
+        if (stats) return launch_chunked_inst<MODE, ACC_, NW_, R_, false, true>(tm, p, sms, stream);         \
+        return launch_chunked_inst<MODE, ACC_, NW_, R_, false, false>(tm, p, sms, stream);                   \
     } while (0)
     if (g_chunked_f32) {
-        if (R == 8) PLB_DISPATCH(float, 8);
-        PLB_DISPATCH(float, 16);
+        if (geom == 1) PLB_DISPATCH(float, 8, 8);
+        if (geom == 2) PLB_DISPATCH(float, 8, 16);
+        PLB_DISPATCH(float, 16, 8);
     }
-    if (R == 8) PLB_DISPATCH(double, 8);
-    PLB_DISPATCH(double, 16);
+    if (geom == 1) PLB_DISPATCH(double, 8, 8);
+    if (geom == 2) PLB_DISPATCH(double, 8, 16);
+    PLB_DISPATCH(double, 16, 8);
 #undef PLB_DISPATCH
 }
 
@@ -758,7 +759,7 @@ extern "C" {
 int plb_set_tuning(int key, int value)
 {
     switch (key) {
-        case 0: plb::g_chunked_rows = value; return PLB_OK;
+        case 0: plb::g_chunked_geom = value; return PLB_OK;
         case 1: plb::g_chunked_f32 = value; return PLB_OK;
         default: plb::set_error("unknown tuning key %d", key); return PLB_ERR_INVALID_ARGUMENT;
     }

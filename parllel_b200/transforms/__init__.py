@@ -4,11 +4,13 @@ from .clip_rewards import ClipRewards
 from .norm_advantage import NormalizeAdvantage
 from .norm_obs import NormalizeObservations
 from .norm_rewards import NormalizeRewards
+from .pipeline import FusedBatchTransforms
 from .running_mean_std import RunningMeanStd
 from .transform import Transform
 
 __all__ = [
     "EstimateAdvantage",
+    "FusedBatchTransforms",
     "ClipRewards",
     "NormalizeAdvantage",
     "NormalizeObservations",

@@ -1,0 +1,198 @@
+"""Fused execution of the sampler's batch-transform list.
+
+The samplers run ``for transform in batch_transforms: sample_tree = transform(sample_tree)``
+(parllel/samplers/basic.py:124-125).  ``FusedBatchTransforms`` is itself a ``Transform`` that
+takes such a list -- the chain the examples build, in this order, every element optional:
+
+    NormalizeRewards -> ClipRewards -> EstimateAdvantage -> NormalizeAdvantage
+
+and runs it as ONE C call (``plb_batch_pipeline_f32``, csrc/plb_pipeline.cu): the reward
+rescale/clip rides on the advantage scan's load path and the advantage moments on its store path,
+so the batch is streamed 3 times instead of 6.  Results are those of calling the transforms one
+after the other; the wrapped transform objects keep owning their state (``return_statistics``).
+On device-resident trees the launch sequence is captured into a CUDA graph per set of leaf
+addresses and replayed, which removes the host launch cost from the sampler loop.
+
+Pass ``[FusedBatchTransforms(batch_transforms)]`` to the sampler instead of ``batch_transforms``.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from .. import _lib
+from .._leaves import Staging, previous_row, rows_2d, stream_ptr
+from .advantage import EstimateAdvantage
+from .clip_rewards import ClipRewards
+from .norm_advantage import EPSILON as ADV_EPSILON
+from .norm_advantage import NormalizeAdvantage
+from .norm_rewards import EPSILON as REWARD_EPSILON
+from .norm_rewards import NormalizeRewards
+from .transform import Transform
+
+_ORDER = (NormalizeRewards, ClipRewards, EstimateAdvantage, NormalizeAdvantage)
+
+
+class FusedBatchTransforms(Transform):
+    def __init__(self, transforms, use_cuda_graph: bool = True, group=None) -> None:
+        self.transforms = list(transforms)
+        self.norm_rewards = self.clip = self.estimate = self.norm_adv = None
+        slot = -1
+        for tf in self.transforms:
+            kind = next((i for i, cls in enumerate(_ORDER) if isinstance(tf, cls)), None)
+            if kind is None or kind <= slot:
+                raise ValueError(
+                    "FusedBatchTransforms handles [NormalizeRewards, ClipRewards, EstimateAdvantage, "
+                    f"NormalizeAdvantage] in that order (each optional); got {type(tf).__name__} out of place")
+            slot = kind
+            if kind == 0:
+                self.norm_rewards = tf
+            elif kind == 1:
+                self.clip = tf
+            elif kind == 2:
+                self.estimate = tf
+            else:
+                self.norm_adv = tf
+        if self.norm_adv is not None and self.norm_adv.multiagent:
+            raise ValueError("multi-agent advantage is not handled by the fused chain")
+        self.use_cuda_graph = use_cuda_graph
+        self.group = group  # torch.distributed group for B-sharded operation (None = default / single GPU)
+        self._ws = None
+        self._moments = None
+        self._graphs: dict = {}
+        self._seen: set = set()
+
+    # ------------------------------------------------------------------------------------
+    def _distributed(self) -> bool:
+        import torch.distributed as dist
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
+
+    def _exchange(self, moments: torch.Tensor) -> None:
+        from ..distributed import all_gather_moments, merge_gathered_moments
+        gathered = all_gather_moments(moments, self.group)
+        merge_gathered_moments(gathered, 1, 0, moments)
+
+    def __call__(self, sample_tree, phases: int = _lib.PHASE_ALL):
+        nr, est, na = self.norm_rewards, self.estimate, self.norm_adv
+        lib = _lib.load()
+        st = Staging(nr.return_statistics.device if nr is not None else None)
+        d = _lib.BatchPipeline()
+        keep = []  # tensors that must outlive the launch
+
+        reward_leaf = sample_tree["reward"] if (nr or self.clip or est) else None
+        reward = st.view(reward_leaf, writeback=bool(nr or self.clip)) if reward_leaf is not None else None
+        done = st.view(sample_tree["done"]) if (nr or est) else None
+        ref = reward if reward is not None else st.view(sample_tree["advantage"], writeback=True)
+        if ref.dim() != 2:
+            raise ValueError("the fused chain needs [T, B] leaves")
+        T, B = ref.shape
+        d.T, d.B = T, B
+        if reward is not None:
+            d.reward, d.ld_reward, _ = rows_2d(reward)
+        if done is not None:
+            d.done, d.ld_done, _ = rows_2d(done)
+        valid = None
+        if (nr is not None and nr.only_valid) or (na is not None and na.only_valid):
+            valid = st.view(sample_tree["valid"])
+            d.valid, d.ld_valid, _ = rows_2d(valid)
+
+        past = None
+        if nr is not None:
+            past_leaf = sample_tree["past_return"]
+            past = st.view(past_leaf, writeback=True)
+            d.past_return, d.ld_past_return, _ = rows_2d(past)
+            prev_ret = previous_row(past_leaf, st)
+            prev_done = previous_row(sample_tree["done"], st)
+            if prev_ret is None:
+                if nr._carry_return is None:
+                    nr._carry_return = torch.zeros(B, dtype=torch.float32, device=st.device)
+                prev_ret = nr._carry_return
+            if prev_done is None:
+                if nr._carry_done is None:
+                    nr._carry_done = torch.zeros(B, dtype=torch.bool, device=st.device)
+                prev_done = nr._carry_done
+            prev_ret, prev_done = prev_ret.reshape(-1).contiguous(), prev_done.reshape(-1).contiguous()
+            keep += [prev_ret, prev_done]
+            d.previous_return, d.previous_done = prev_ret.data_ptr(), prev_done.data_ptr()
+            stats = nr.return_statistics
+            d.return_mean, d.return_var = stats.mean_tensor.data_ptr(), stats.var_tensor.data_ptr()
+            d.return_count = stats.count_tensor.data_ptr()
+            d.normalize_rewards = 1
+            d.discount = float(nr.discount)
+        if self.clip is not None:
+            d.clip_rewards = 1
+            d.clip_lo = _lib.NAN if self.clip.reward_min is None else float(self.clip.reward_min)
+            d.clip_hi = _lib.NAN if self.clip.reward_max is None else float(self.clip.reward_max)
+        if est is not None:
+            value = st.view(sample_tree["agent_info"]["value"])
+            boot = st.view(sample_tree["bootstrap_value"]).reshape(-1).contiguous()
+            adv = st.view(sample_tree["advantage"], writeback=True)
+            ret = st.view(sample_tree["return_"], writeback=True)
+            if value.dim() != 2:
+                raise ValueError("the fused chain needs a [T, B] value estimate (no trailing agent axis)")
+            keep.append(boot)
+            d.value, d.ld_value, _ = rows_2d(value)
+            d.bootstrap_value = boot.data_ptr()
+            d.advantage, d.ld_advantage, _ = rows_2d(adv)
+            d.return_, d.ld_return, _ = rows_2d(ret)
+            d.estimate_advantage = 1
+            if nr is not None and float(est.discount) != float(nr.discount):
+                raise ValueError("NormalizeRewards and EstimateAdvantage must share the discount in the fused chain")
+            d.discount = float(est.discount)
+            d.gae_lambda = float(est.gae_lambda)
+        elif na is not None:
+            adv = ref if reward is None else st.view(sample_tree["advantage"], writeback=True)
+            d.advantage, d.ld_advantage, _ = rows_2d(adv)
+        if na is not None:
+            d.normalize_advantage = 1
+        d.eps_reward, d.eps_advantage = REWARD_EPSILON, ADV_EPSILON
+        d.moments_flags = _lib.MOMENTS_F32_FLOW
+
+        dev = st.device
+        if self._ws is None or self._ws.device != dev:
+            self._ws = torch.zeros(lib.plb_batch_pipeline_workspace_bytes(), dtype=torch.uint8, device=dev)
+            self._moments = torch.zeros(6, dtype=torch.float64, device=dev)
+        d.return_moments = self._moments.data_ptr()
+        d.advantage_moments = self._moments.data_ptr() + 24
+        d.workspace, d.workspace_bytes = self._ws.data_ptr(), self._ws.numel()
+
+        def enqueue():
+            s = stream_ptr(dev)
+            if self._distributed():
+                _lib.check(lib.plb_batch_pipeline_f32(ctypes.byref(d), _lib.PHASE_A, s), "fused transforms (A)")
+                if nr is not None:
+                    self._exchange(self._moments[0:3])
+                _lib.check(lib.plb_batch_pipeline_f32(ctypes.byref(d), _lib.PHASE_B, s), "fused transforms (B)")
+                if na is not None:
+                    self._exchange(self._moments[3:6])
+                _lib.check(lib.plb_batch_pipeline_f32(ctypes.byref(d), _lib.PHASE_C, s), "fused transforms (C)")
+            else:
+                _lib.check(lib.plb_batch_pipeline_f32(ctypes.byref(d), phases, s), "fused transforms")
+            if nr is not None and T > 0:
+                if nr._carry_return is not None:
+                    nr._carry_return.copy_(past[T - 1])
+                if nr._carry_done is not None:
+                    nr._carry_done.copy_(done[T - 1])
+
+        graphable = (self.use_cuda_graph and not st.staged and not self._distributed())
+        if not graphable:
+            enqueue()
+        else:
+            key = bytes(d) + bytes([phases])
+            graph = self._graphs.get(key)
+            if graph is not None:
+                graph[0].replay()
+            elif key not in self._seen:
+                self._seen.add(key)  # first sight: run eagerly (also configures the kernels)
+                enqueue()
+            else:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    enqueue()
+                g.replay()
+                if len(self._graphs) > 64:
+                    self._graphs.clear()
+                self._graphs[key] = (g, keep, d)
+        st.finish()
+        return sample_tree

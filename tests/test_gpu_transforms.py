@@ -69,6 +69,86 @@ def test_batch_transform_pipeline_matches_reference(golden, name, leaves):
         np.testing.assert_allclose([st.mean, st.var, st.count], g[f"b{it}_out_stats"], rtol=2e-6)
 
 
+@pytest.mark.parametrize("name", ["pipeline_c0", "pipeline_valid", "pipeline_lambda1"])
+@pytest.mark.parametrize("leaves", ["device_array", "plain_tensor", "host_numpy"])
+@pytest.mark.parametrize("graph", [False, True])
+def test_fused_batch_transforms_match_reference(golden, name, leaves, graph):
+    """The same chain through FusedBatchTransforms (one C call, optional CUDA graph replay)."""
+    from parllel_b200 import ArrayDict
+    from parllel_b200.transforms import (ClipRewards, EstimateAdvantage, FusedBatchTransforms, NormalizeAdvantage,
+                                         NormalizeRewards)
+    g = golden(name)
+    T, B, p_done, n_batches, with_valid, lam, clip_lo, clip_hi, init_count = g["meta"]
+    T, B, with_valid = int(T), int(B), bool(with_valid)
+    tree = _make_device_tree(T, B, with_valid)
+    if leaves != "device_array":
+        tree = ArrayDict({k: (v if isinstance(v, (torch.Tensor, ArrayDict)) else v.tensor) for k, v in tree.items()})
+        tree["agent_info"] = ArrayDict({"value": tree["agent_info"]["value"].tensor})
+    if leaves == "host_numpy":
+        tree = tree.apply(lambda t: t.cpu().numpy())
+    fused = FusedBatchTransforms([
+        NormalizeRewards(tree, discount=0.99, initial_count=None if init_count < 0 else init_count),
+        ClipRewards(reward_min=clip_lo, reward_max=clip_hi),
+        EstimateAdvantage(discount=0.99, gae_lambda=lam),
+        NormalizeAdvantage(tree),
+    ], use_cuda_graph=graph)
+    reps = 3 if (graph and leaves == "plain_tensor") else 1  # replays must not depend on stale state
+    for it in range(int(n_batches)):
+        if leaves == "device_array":
+            tree.rotate()
+        for rep in range(reps):
+            if rep > 0:  # undo the state side effects so the same batch can be replayed through the graph
+                fused.norm_rewards.return_statistics.load_state(*saved_stats)
+                fused.norm_rewards._carry_return.copy_(saved_carry[0])
+                fused.norm_rewards._carry_done.copy_(saved_carry[1])
+            elif leaves == "plain_tensor" and fused.norm_rewards._carry_return is not None:
+                saved_carry = (fused.norm_rewards._carry_return.clone(), fused.norm_rewards._carry_done.clone())
+            if rep == 0:
+                st0 = fused.norm_rewards.return_statistics
+                saved_stats = (st0.mean.copy(), st0.var.copy(), float(st0.count))
+                if leaves == "plain_tensor" and fused.norm_rewards._carry_return is None:
+                    saved_carry = (torch.zeros(B, device="cuda"), torch.zeros(B, dtype=torch.bool, device="cuda"))
+            for k, src in (("reward", "reward"), ("done", "done"), ("bootstrap_value", "bootstrap_value")):
+                val = g[f"b{it}_in_{src}"]
+                tree[k][...] = val if leaves == "host_numpy" else torch.from_numpy(val).cuda()
+            val = g[f"b{it}_in_value"]
+            tree["agent_info"]["value"][...] = val if leaves == "host_numpy" else torch.from_numpy(val).cuda()
+            if with_valid:
+                val = g[f"b{it}_in_valid"]
+                tree["valid"][...] = val if leaves == "host_numpy" else torch.from_numpy(val).cuda()
+            assert fused(tree) is tree
+        for k in ("past_return", "reward", "return_", "advantage"):
+            leaf = tree[k]
+            got = leaf.cpu().numpy() if isinstance(leaf, torch.Tensor) else np.asarray(leaf)
+            assert_within_tolerance(got, g[f"b{it}_out_{k}"], what=f"{name} batch {it} {k}")
+        st = fused.norm_rewards.return_statistics
+        np.testing.assert_allclose([st.mean, st.var, st.count], g[f"b{it}_out_stats"], rtol=2e-6)
+
+
+def test_fused_subsets_and_order_errors():
+    from parllel_b200.transforms import ClipRewards, EstimateAdvantage, FusedBatchTransforms, NormalizeAdvantage
+    with pytest.raises(ValueError):
+        FusedBatchTransforms([EstimateAdvantage(0.99, 0.95), ClipRewards(-1, 1)])
+    T, B = 200, 48
+    batch = make_batch(np.random.default_rng(4), T, B, 0.03)
+    dev = {k: torch.from_numpy(v).cuda() for k, v in batch.items()}
+    def tree():
+        return {"reward": dev["reward"].clone(), "done": dev["done"], "agent_info": {"value": dev["value"]},
+                "bootstrap_value": dev["bootstrap_value"], "advantage": torch.zeros(T, B, device="cuda"),
+                "return_": torch.zeros(T, B, device="cuda")}
+    a, b = tree(), tree()
+    seq = [ClipRewards(-0.5, None), EstimateAdvantage(0.99, 0.9), NormalizeAdvantage(a)]
+    for tf in seq:
+        tf(a)
+    FusedBatchTransforms([ClipRewards(-0.5, None), EstimateAdvantage(0.99, 0.9), NormalizeAdvantage(b)])(b)
+    for k in ("reward", "advantage", "return_"):
+        assert_within_tolerance(b[k].cpu().numpy(), a[k].cpu().numpy(), what=k)
+    c = tree()
+    FusedBatchTransforms([EstimateAdvantage(0.99, 0.9)])(c)
+    EstimateAdvantage(0.99, 0.9)(a := tree())
+    assert torch.equal(c["advantage"], a["advantage"]) and torch.equal(c["return_"], a["return_"])
+
+
 @pytest.mark.parametrize("name", ["norm_obs", "norm_obs_valid"])
 def test_normalize_observations_matches_reference(golden, name):
     from parllel_b200 import ArrayDict, DeviceArray

@@ -19,16 +19,22 @@ from parllel_b200.transforms import (EstimateAdvantage, NormalizeAdvantage,  # n
                                      NormalizeObservations, NormalizeRewards)
 
 
-def timed(fn, reps, flush=None):
+def timed(fn, reps, flush=None, inner=1):
+    """Per-launch time in us.  inner == 1: one event pair per launch after an L2 flush (event
+    resolution on this box is ~2 us); inner > 1: `inner` back-to-back launches per event pair
+    (callers rotate buffer sets larger than L2 through `i`)."""
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    k = 0
     for i in range(reps):
-        if flush is not None:
+        if flush is not None and inner == 1:
             flush.zero_()
         ev[i][0].record()
-        fn(i)
+        for _ in range(inner):
+            fn(k)
+            k += 1
         ev[i][1].record()
     torch.cuda.synchronize()
-    return [a.elapsed_time(b) * 1e3 for a, b in ev]
+    return [a.elapsed_time(b) * 1e3 / inner for a, b in ev]
 
 
 def main():
@@ -40,6 +46,7 @@ def main():
     ap.add_argument("--lam", type=float, default=0.95)
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--n", type=int, default=16384)
+    ap.add_argument("--inner", type=int, default=1, help="launches per event pair (rotating buffer sets)")
     ap.add_argument("--rows", type=int, default=0)
     ap.add_argument("--f32", type=int, default=0)
     args = ap.parse_args()
@@ -52,22 +59,27 @@ def main():
     flush = torch.empty(256 * 2**20, dtype=torch.uint8, device=dev)  # > L2
     T, B = args.T, args.B
     if args.what in ("gae", "normadv", "past"):
-        t = {"reward": torch.randn(T, B, device=dev), "done": torch.rand(T, B, device=dev) < 0.01,
-             "agent_info": {"value": torch.randn(T, B, device=dev)}, "bootstrap_value": torch.randn(B, device=dev),
-             "advantage": torch.empty(T, B, device=dev), "return_": torch.empty(T, B, device=dev),
-             "past_return": torch.empty(T, B, device=dev)}
-        tree = ArrayDict(t)
+        n_sets = 1 if args.inner == 1 else max(2, int(np.ceil(2.5 * 126 * 2**20 / (17 * T * B))))
+        trees = []
+        for _ in range(n_sets):
+            t = {"reward": torch.randn(T, B, device=dev), "done": torch.rand(T, B, device=dev) < 0.01,
+                 "agent_info": {"value": torch.randn(T, B, device=dev)}, "bootstrap_value": torch.randn(B, device=dev),
+                 "advantage": torch.empty(T, B, device=dev), "return_": torch.empty(T, B, device=dev),
+                 "past_return": torch.empty(T, B, device=dev)}
+            trees.append(ArrayDict(t))
+        tree = trees[0]
         if args.what == "gae":
             tf = EstimateAdvantage(0.99, args.lam, algo=args.algo)
             nbytes = 17 * T * B
         elif args.what == "normadv":
-            EstimateAdvantage(0.99, args.lam, algo=args.algo)(tree)
+            for tr in trees:
+                EstimateAdvantage(0.99, args.lam, algo=args.algo)(tr)
             tf = NormalizeAdvantage(tree)
             nbytes = 12 * T * B
         else:
             tf = NormalizeRewards(tree, 0.99, algo=args.algo)
             nbytes = 17 * T * B
-        us = timed(lambda i: tf(tree), args.reps, flush)
+        us = timed(lambda i: tf(trees[i % n_sets]), args.reps, flush, args.inner)
     elif args.what == "norm_obs":
         B, shape = 1024, (3, 84, 84)
         obs = torch.randn((4, B) + shape, device=dev) * 3 + 5
