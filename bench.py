@@ -200,8 +200,9 @@ def main():
     import torch
     import torch.distributed as dist
 
-    from parllel_b200 import ArrayDict
-    from parllel_b200.transforms import EstimateAdvantage, NormalizeAdvantage
+    from parllel_b200 import ArrayDict, _lib
+    from parllel_b200.host_pipeline import PinnedBatch
+    from parllel_b200.transforms import EstimateAdvantage, FusedBatchTransforms, NormalizeAdvantage
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device"
     torch.cuda.set_device(local_rank)
@@ -221,18 +222,15 @@ def main():
         sets.append(ArrayDict({"reward": t["reward"], "done": t["done"], "agent_info": {"value": t["value"]},
                                "bootstrap_value": t["bootstrap_value"],
                                "advantage": torch.empty_like(t["value"]), "return_": torch.empty_like(t["value"])}))
-    ea = EstimateAdvantage(GAMMA, LAMBDA, algo="chunked")
-    na = NormalizeAdvantage(sets[0]) if not distributed else None
-    if distributed:
-        from parllel_b200.distributed import ShardedNormalizeAdvantage
-        na = ShardedNormalizeAdvantage(sets[0])
+
+    # the public API: the sampler's batch_transforms list, fused (one C call, CUDA-graph replay on 1 GPU;
+    # phase-split with an NCCL all-gather of the (count, mean, M2) moments when B is sharded over ranks)
+    fused = FusedBatchTransforms([EstimateAdvantage(GAMMA, LAMBDA), NormalizeAdvantage(sets[0])])
 
     def step(i):
-        tree = sets[i % n_sets]
-        ea(tree)
-        na(tree)
+        fused(sets[i % n_sets])
 
-    for i in range(warmup):
+    for i in range(max(warmup, 3 * n_sets)):  # every buffer set: eager pass, capture pass, replay pass
         step(i)
     torch.cuda.synchronize()
     if distributed:
@@ -241,44 +239,56 @@ def main():
 
     stream = torch.cuda.current_stream(dev)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    k_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     with ClockSampler(local_rank) as clocks:
         ev0.record(stream)
         for i in range(args.steps):
-            tree = sets[i % n_sets]
-            k_ev[i][0].record(stream)
-            ea(tree)
-            k_ev[i][1].record(stream)
-            na(tree)
+            step(i)
         ev1.record(stream)
         torch.cuda.synchronize()
-        if args.steps * 0.03 < 300:  # keep the GPU busy long enough for >= a few clock samples
-            t_end = time.perf_counter() + 0.4
-            j = 0
-            while time.perf_counter() < t_end:
-                step(j)
-                j += 1
-            torch.cuda.synchronize()
+        elapsed_ms = ev0.elapsed_time(ev1)
+
+        # dominant kernel alone (phase B of the same chain = the GAE scan with fused advantage moments):
+        # one launch per buffer set captured into a CUDA graph, replayed until `steps` launches have run
+        raw = FusedBatchTransforms([EstimateAdvantage(GAMMA, LAMBDA), NormalizeAdvantage(sets[0])], use_cuda_graph=False)
+        for i in range(n_sets):
+            raw(sets[i], phases=_lib.PHASE_B)
+        torch.cuda.synchronize()
+        kgraph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(kgraph):
+            for i in range(n_sets):
+                raw(sets[i], phases=_lib.PHASE_B)
+        kgraph.replay()
+        torch.cuda.synchronize()
+        n_replays = max(1, args.steps // n_sets)
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record(stream)
+        for _ in range(n_replays):
+            kgraph.replay()
+        k1.record(stream)
+        torch.cuda.synchronize()
+        kernel_launches = n_replays * n_sets
+        gae_us = k0.elapsed_time(k1) * 1e3 / kernel_launches
+
+        t_end = time.perf_counter() + 0.5  # keep the GPU under the same load for a few clock samples
+        j = 0
+        while time.perf_counter() < t_end:
+            step(j)
+            j += 1
+        torch.cuda.synchronize()
     if distributed:
         dist.barrier()
-    elapsed_ms = ev0.elapsed_time(ev1)
-    gae_ms = [a.elapsed_time(b) for a, b in k_ev]
-    if distributed:
         tmax = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         elapsed_ms = float(tmax.item())
     transitions = T_STEPS * B_ENVS * world * args.steps
     value = transitions / (elapsed_ms * 1e-3)
 
-    # ---- e2e: public API with HOST leaves (pinned), H2D + kernels + D2H per step --------------
-    from parllel_b200.host_pipeline import PinnedBatch
+    # ---- e2e: the same public API on HOST (pinned numpy) leaves: H2D + kernels + D2H every step ----
     e2e_steps = args.e2e_steps or min(args.steps, 40)
     host_sets = [PinnedBatch(synth_batch(7000 + 10 * rank + i)) for i in range(2)]
-    e2e_ea = EstimateAdvantage(GAMMA, LAMBDA, algo="chunked")
-    e2e_na = NormalizeAdvantage(host_sets[0].tree) if not distributed else na.__class__(host_sets[0].tree)
+    e2e_fused = FusedBatchTransforms([EstimateAdvantage(GAMMA, LAMBDA), NormalizeAdvantage(host_sets[0].tree)])
     for i in range(3):
-        t = host_sets[i % 2].tree
-        e2e_na(e2e_ea(t))
+        e2e_fused(host_sets[i % 2].tree)
     torch.cuda.synchronize()
     if distributed:
         dist.barrier()
@@ -286,8 +296,7 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for i in range(e2e_steps):
-        t = host_sets[i % 2].tree
-        e2e_na(e2e_ea(t))
+        e2e_fused(host_sets[i % 2].tree)
     e1.record(stream)
     torch.cuda.synchronize()
     e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
@@ -296,8 +305,8 @@ def main():
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         e2e_ms = float(tmax.item())
     e2e_value = T_STEPS * B_ENVS * world * e2e_steps / (e2e_ms * 1e-3)
-    h2d = T_STEPS * B_ENVS * 9 + B_ENVS * 4
-    d2h = T_STEPS * B_ENVS * 8 * 2  # advantage crosses twice on the unfused host path (GAE, then normalise)
+    h2d = T_STEPS * B_ENVS * 9 + B_ENVS * 4   # reward, value, done, bootstrap_value
+    d2h = T_STEPS * B_ENVS * 8                # advantage, return_
 
     if rank != 0:
         if distributed:
@@ -305,8 +314,7 @@ def main():
         return
 
     peak, peak_src = measured_peak()
-    gae_s = statistics.mean(gae_ms) * 1e-3
-    achieved = T_STEPS * B_ENVS * GAE_BYTES_PER_TRANSITION / gae_s / 1e9
+    achieved = T_STEPS * B_ENVS * GAE_BYTES_PER_TRANSITION / (gae_us * 1e-6) / 1e9
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
         "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -314,13 +322,14 @@ def main():
         "clocks": clocks.summary(),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
-                "api": "EstimateAdvantage.__call__ + NormalizeAdvantage.__call__ on pinned numpy leaves"},
-        "gpu_launches": args.steps * 3,
-        "roofline": {"bound": "hbm", "kernel": "scan_chunked_kernel<GAE> (EstimateAdvantage)",
+                "api": "FusedBatchTransforms([EstimateAdvantage, NormalizeAdvantage])(tree) on pinned numpy leaves"},
+        "gpu_launches": args.steps * 2,
+        "kernels_per_step": ["scan_chunked_kernel<GAE,+moments>", "elementwise_kernel<NormAdvOp>"],
+        "roofline": {"bound": "hbm", "kernel": "plb::chunked::scan_chunked_kernel<MODE=GAE, HAS_STATS> (EstimateAdvantage)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "peak_source": peak_src, "traffic": None,
                      "algorithmic_bytes_per_launch": T_STEPS * B_ENVS * GAE_BYTES_PER_TRANSITION,
-                     "avg_launch_us": gae_s * 1e6,
+                     "avg_launch_us": gae_us, "launches_timed": kernel_launches,
                      "frac_of_nominal_8TBs": achieved / 8000.0},
     }
     if not args.no_cpu_baseline:

@@ -63,6 +63,37 @@ __host__ __device__ __forceinline__ Moments merge(const Moments &a, const Moment
     return r;
 }
 
+// Division-free reduction currency: sums of (x - piv) and (x - piv)^2 over n elements.
+// Two Sums with the same pivot add component-wise; `rebase` moves a Sums to another pivot
+// exactly (up to float64 rounding) without a division, so whole block / grid reductions are
+// plain additions and only the very last thread divides (to_moments).
+struct Sums {
+    double n, s1, s2, piv;
+};
+
+__host__ __device__ __forceinline__ Sums rebase(Sums a, double P)
+{
+    const double d = a.piv - P;
+    a.s2 = a.s2 + 2.0 * d * a.s1 + a.n * d * d;
+    a.s1 = a.s1 + a.n * d;
+    a.piv = P;
+    return a;
+}
+
+__host__ __device__ __forceinline__ Moments to_moments(const Sums &a)
+{
+    Moments m;
+    m.n = a.n;
+    if (a.n == 0.0) {
+        m.mean = 0.0; m.m2 = 0.0;
+    } else {
+        m.mean = a.piv + a.s1 / a.n;
+        m.m2 = a.s2 - a.s1 * a.s1 / a.n;
+        if (m.m2 < 0.0) m.m2 = 0.0;
+    }
+    return m;
+}
+
 // Per-thread accumulator: sums of (x - K) and (x - K)^2 around a pivot K (the first
 // element seen), so the later conversion M2 = s2 - s1^2/n does not cancel.
 struct PivotAcc {
@@ -81,54 +112,59 @@ struct PivotAcc {
         s2 = fma(d, d, s2);
         ++n;
     }
-    __device__ __forceinline__ Moments finish() const
+    __device__ __forceinline__ Sums sums() const
     {
-        Moments m;
-        m.n = (double)n;
-        if (n == 0u) {
-            m.mean = 0.0; m.m2 = 0.0;
-        } else {
-            m.mean = K + s1 / m.n;
-            m.m2 = s2 - s1 * s1 / m.n;
-            if (m.m2 < 0.0) m.m2 = 0.0;
-        }
-        return m;
+        Sums r;
+        r.n = (double)n; r.s1 = s1; r.s2 = s2; r.piv = K;
+        return r;
     }
+    __device__ __forceinline__ Moments finish() const { return to_moments(sums()); }
 };
 
 #ifdef __CUDACC__
-__device__ __forceinline__ Moments shfl_down(const Moments &m, int delta)
-{
-    Moments r;
-    r.n = __shfl_down_sync(0xffffffffu, m.n, delta);
-    r.mean = __shfl_down_sync(0xffffffffu, m.mean, delta);
-    r.m2 = __shfl_down_sync(0xffffffffu, m.m2, delta);
-    return r;
-}
-
-// Fixed-shape tree: lane 0 ends up with merge over lanes in a deterministic order.
-__device__ __forceinline__ Moments warp_merge(Moments m)
-{
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) m = merge(m, shfl_down(m, d));
-    return m;
-}
-
-// Block-wide merge; result valid in thread 0.  `scratch` needs >= 32 Moments.
-__device__ __forceinline__ Moments block_merge(Moments m, Moments *scratch)
+// Block-wide reduction of per-thread Sums without divisions: agree on a pivot (the pivot of the
+// lowest-numbered thread that saw data), rebase, add.  Result valid in thread 0.
+// `scratch` needs >= 32 Sums; all threads of the block must call.
+__device__ __forceinline__ Sums block_reduce_sums(Sums a, Sums *scratch)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nwarps = (blockDim.x + 31) >> 5;
-    m = warp_merge(m);
-    if (lane == 0) scratch[warp] = m;
+    // warp pivot: first lane with data
+    const unsigned has = __ballot_sync(0xffffffffu, a.n > 0.0);
+    const int src = has ? (__ffs(has) - 1) : 0;
+    const double wp = __shfl_sync(0xffffffffu, a.piv, src);
+    if (lane == 0) {
+        scratch[warp].piv = wp;
+        scratch[warp].n = has ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    double P = 0.0;
+    for (int w = 0; w < nwarps; ++w) {
+        if (scratch[w].n > 0.0) { P = scratch[w].piv; break; }
+    }
+    __syncthreads();
+    a = rebase(a, P);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        a.n += __shfl_down_sync(0xffffffffu, a.n, d);
+        a.s1 += __shfl_down_sync(0xffffffffu, a.s1, d);
+        a.s2 += __shfl_down_sync(0xffffffffu, a.s2, d);
+    }
+    if (lane == 0) scratch[warp] = a;
     __syncthreads();
     if (warp == 0) {
-        Moments z;
-        z.n = 0.0; z.mean = 0.0; z.m2 = 0.0;
-        m = (lane < nwarps) ? scratch[lane] : z;
-        m = warp_merge(m);
+        Sums z;
+        z.n = 0.0; z.s1 = 0.0; z.s2 = 0.0; z.piv = P;
+        a = (lane < nwarps) ? scratch[lane] : z;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            a.n += __shfl_down_sync(0xffffffffu, a.n, d);
+            a.s1 += __shfl_down_sync(0xffffffffu, a.s1, d);
+            a.s2 += __shfl_down_sync(0xffffffffu, a.s2, d);
+        }
+        a.piv = P;
     }
-    return m;
+    return a;
 }
 
 __device__ __forceinline__ bool is_nan_bound(double b) { return b != b; }

@@ -250,7 +250,7 @@ scan_chunked_kernel(const __grid_constant__ TensorMaps tm, const Params p)
     StageT *stages = reinterpret_cast<StageT *>(smem_raw);
     OutT *outs = reinterpret_cast<OutT *>(smem_raw + sizeof(StageT) * p.n_stages);
     SharedT *sh = reinterpret_cast<SharedT *>(smem_raw + sizeof(StageT) * p.n_stages + 2 * sizeof(OutT));
-    __shared__ Moments red_scratch[32];
+    __shared__ Sums red_scratch[32];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_stages = p.n_stages, n_chunks = p.n_chunks, n_strips = p.n_strips;
@@ -316,8 +316,12 @@ scan_chunked_kernel(const __grid_constant__ TensorMaps tm, const Params p)
         clip_hi = p.clip_hi;
     }
 
-    Moments acc;  // fused statistics of out0 (HAS_STATS)
-    acc.n = 0.0; acc.mean = 0.0; acc.m2 = 0.0;
+    // fused statistics of out0 (HAS_STATS): per-thread sums of (y - K) and (y - K)^2 around a pivot K
+    // (the first value the thread produces); float32 inside a tile, float64 across tiles
+    float st_piv = 0.f;
+    bool st_has = false;
+    double st_s1 = 0.0, st_s2 = 0.0;
+    unsigned st_n = 0;
 
     int stage = 0, par = 0;
     uint32_t phase = 0;
@@ -325,6 +329,7 @@ scan_chunked_kernel(const __grid_constant__ TensorMaps tm, const Params p)
     for (int strip = blockIdx.x; strip < n_strips; strip += gridDim.x) {
         const int64_t col = (int64_t)strip * W + lane;
         const bool col_ok = col < p.B;
+        const bool strip_full = (int64_t)(strip + 1) * W <= p.B;
         ACC carry0;  // scan value entering the first tile of the strip, per column
         if (MODE == 0) carry0 = (ACC)0;
         else if (MODE == 1) carry0 = col_ok ? (ACC)p.boot[col] : (ACC)0;
@@ -423,9 +428,14 @@ scan_chunked_kernel(const __grid_constant__ TensorMaps tm, const Params p)
             }
 
             // pass 2: finalise from registers into the output staging tile
+            // (statistics: interior tiles without a mask take a predicate-free path)
+            const bool stats_fast = HAS_STATS && p.valid == nullptr && strip_full && t0 >= 0 && t0 + TC <= T;
+            const int u_lo = (int)((t0 + i0 < 0) ? -(t0 + i0) : 0);                  // first row of this warp inside [0, T)
+            const int u_hi = (int)((T - (t0 + i0) < R) ? (T - (t0 + i0)) : R);       // one past the last
             const uint8_t *vp = (HAS_STATS && p.valid != nullptr) ? p.valid + (t0 + i0) * p.ld_valid + col : nullptr;
-            float s1 = 0.f, s2 = 0.f, piv = 0.f;  // float32 micro-accumulation of this tile's outputs
-            unsigned cnt = 0;
+            float s1 = 0.f, s2 = 0.f;  // float32 micro-accumulation of this tile's outputs
+            float ystat[HAS_STATS ? R : 1];
+            (void)ystat;
 #pragma unroll
             for (int u = 0; u < R; ++u) {
                 const float x = to_f32(fma(C[u], cin, A[u]));
@@ -442,25 +452,39 @@ scan_chunked_kernel(const __grid_constant__ TensorMaps tm, const Params p)
                     y0 = x;
                     O.o[0][i0 + u][lane] = x;
                 }
-                if (HAS_STATS) {
-                    const bool ok = col_ok && (uint64_t)(t0 + i0 + u) < (uint64_t)T;
-                    if (ok && (vp == nullptr || *vp != 0)) {
-                        if (cnt == 0) piv = y0;
-                        const float d = y0 - piv;
+                if (HAS_STATS) ystat[u] = y0;
+            }
+            if (HAS_STATS) {
+                if (!st_has) {  // pivot: any value of the data's magnitude will do
+                    st_piv = ystat[0];
+                    st_has = true;
+                }
+                if (stats_fast) {
+#pragma unroll
+                    for (int u = 0; u < R; ++u) {
+                        const float d = ystat[u] - st_piv;
                         s1 += d;
                         s2 = fmaf(d, d, s2);
-                        ++cnt;
                     }
-                    if (vp != nullptr) vp += p.ld_valid;
+                } else {
+#pragma unroll
+                    for (int u = 0; u < R; ++u) {
+                        const float d = ystat[u] - st_piv;
+                        bool ok = col_ok && u >= u_lo && u < u_hi;
+                        if (ok && vp != nullptr) ok = vp[(int64_t)u * p.ld_valid] != 0;
+                        if (ok) {
+                            s1 += d;
+                            s2 = fmaf(d, d, s2);
+                            ++st_n;
+                        }
+                    }
                 }
             }
             fence_proxy_async_smem();  // staging-tile writes -> visible to the TMA store issued after the next barrier
-            if (HAS_STATS && cnt != 0) {
-                Moments m;
-                m.n = (double)cnt;
-                m.mean = (double)piv + (double)s1 / m.n;
-                m.m2 = fmax((double)s2 - (double)s1 * (double)s1 / m.n, 0.0);
-                acc = merge(acc, m);
+            if (HAS_STATS) {
+                if (stats_fast) st_n += R;
+                st_s1 += (double)s1;
+                st_s2 += (double)s2;
             }
 
             par ^= 1;
@@ -473,7 +497,11 @@ scan_chunked_kernel(const __grid_constant__ TensorMaps tm, const Params p)
         if (st_pending) store_tile(par ^ 1);
         tma_store_wait<0>();  // smem must stay alive (and global writes complete) before the CTA retires
     }
-    if (HAS_STATS) moments_tail(acc, p.tail, red_scratch);
+    if (HAS_STATS) {
+        Sums acc;
+        acc.n = (double)st_n; acc.s1 = st_s1; acc.s2 = st_s2; acc.piv = (double)st_piv;
+        moments_tail(acc, p.tail, red_scratch);
+    }
 }
 
 }  // namespace chunked
@@ -545,10 +573,17 @@ static int launch_chunked_inst(const chunked::TensorMaps &tm, chunked::Params p,
     // 228 KB of shared memory per SM, 1 KB reserved per CTA, ~1 KB of static scratch per CTA.
     int ctas_per_sm = p.n_strips <= sms ? 1 : (p.n_strips <= 2 * sms ? 2 : 3);
     if (NW > 8) ctas_per_sm = 1;
-    const size_t smem_cap = 227 * 1024 - 1024;
+    auto kern = scan_chunked_kernel<MODE, ACC, NW, R, HAS_PRE, HAS_STATS>;
+    static thread_local size_t static_smem = ~(size_t)0;
+    if (static_smem == ~(size_t)0) {
+        cudaFuncAttributes attr;
+        PLB_CUDA(cudaFuncGetAttributes(&attr, kern));
+        static_smem = attr.sharedSizeBytes;
+    }
+    const size_t smem_cap = 227 * 1024 - static_smem;  // per-CTA limit: static + dynamic <= 227 KB
     int stages = 0;
     for (; ctas_per_sm >= 1; --ctas_per_sm) {
-        size_t budget = (size_t)(228 * 1024) / ctas_per_sm - 2048;
+        size_t budget = (size_t)(228 * 1024) / ctas_per_sm - 1024 - static_smem;  // 1 KB reserved per CTA
         if (budget > smem_cap) budget = smem_cap;
         stages = budget > fixed_bytes ? (int)((budget - fixed_bytes) / stage_bytes) : 0;
         if (stages >= 2 || ctas_per_sm == 1) break;
@@ -559,7 +594,6 @@ static int launch_chunked_inst(const chunked::TensorMaps &tm, chunked::Params p,
     p.n_stages = stages;
     const size_t smem = stage_bytes * stages + fixed_bytes;
     const int grid = p.n_strips < sms * ctas_per_sm ? p.n_strips : sms * ctas_per_sm;
-    auto kern = scan_chunked_kernel<MODE, ACC, NW, R, HAS_PRE, HAS_STATS>;
     static thread_local bool configured = false;
     if (!configured) {
         PLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
@@ -589,10 +623,11 @@ static int launch_chunked(const ChunkedIO &io, chunked::Params p, bool has_pre, 
     using namespace chunked;
     const int sms = sm_count();
     PLB_REQUIRE(sms > 0, PLB_ERR_UNSUPPORTED, "no CUDA device");
-    // one CTA per SM (few strips): 16 warps x 8 rows = 128-row tiles, all the latency hiding one CTA
-    // can get; several CTAs per SM (many strips): 8 warps x 8 rows = 64-row tiles.
+    // one CTA per SM (few strips): 8 warps x 16 rows = 128-row tiles (measured fastest at C1: 13.8 us
+    // vs 15.2 us for 16 warps x 8 rows and 18.3 us for 64-row tiles); several CTAs per SM (many
+    // strips): 8 warps x 8 rows = 64-row tiles.
     int geom = g_chunked_geom;
-    if (geom == 0) geom = (p.T <= 64 || ceil_div(p.B, W) > sms) ? 1 : 3;
+    if (geom == 0) geom = (p.T <= 64 || ceil_div(p.B, W) > sms) ? 1 : 2;
     if (p.T <= 64) geom = 1;
     const int TC = geom == 1 ? 64 : 128;
     TensorMaps tm;

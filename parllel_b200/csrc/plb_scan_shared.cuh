@@ -14,11 +14,11 @@ namespace plb {
 //   [64, 64 + 24*MAX)  per-CTA partial moments
 // ---------------------------------------------------------------------------------
 constexpr int MOMENTS_MAX_PARTIALS = 4096;
-constexpr size_t MOMENTS_WS_BYTES = 64 + sizeof(Moments) * MOMENTS_MAX_PARTIALS;
+constexpr size_t MOMENTS_WS_BYTES = 64 + sizeof(Sums) * MOMENTS_MAX_PARTIALS;
 
 struct MomentsTail {
     double *moments_out;  // [3] = (count, mean, M2); nullptr disables the tail
-    Moments *partials;
+    Sums *partials;
     unsigned *ticket;
 };
 
@@ -27,7 +27,7 @@ static inline MomentsTail make_tail(double *moments_out, void *workspace)
     MomentsTail t;
     t.moments_out = moments_out;
     t.ticket = reinterpret_cast<unsigned *>(workspace);
-    t.partials = reinterpret_cast<Moments *>(reinterpret_cast<unsigned char *>(workspace) + 64);
+    t.partials = reinterpret_cast<Sums *>(reinterpret_cast<unsigned char *>(workspace) + 64);
     return t;
 }
 
@@ -162,17 +162,18 @@ __device__ __forceinline__ void bulk_store_1d(void *dst, const void *src, uint32
 }
 
 // ---------------------------------------------------------------------------------
-// Grid-wide moments tail: every CTA contributes one partial; the last CTA to arrive
-// merges all partials in index order (deterministic) and writes (count, mean, M2).
-// Must be called by ALL threads of EVERY CTA of the grid.  `scratch` >= 32 Moments.
+// Grid-wide moments tail: every CTA contributes one partial (division-free Sums); the last CTA
+// to arrive rebases all partials to one pivot, adds them in a fixed order (deterministic) and
+// performs the only divisions of the whole reduction to write (count, mean, M2).
+// Must be called by ALL threads of EVERY CTA of the grid.  `scratch` >= 32 Sums.
 // ---------------------------------------------------------------------------------
-__device__ __forceinline__ void moments_tail(Moments mine, const MomentsTail &tail, Moments *scratch)
+__device__ __forceinline__ void moments_tail(const Sums &mine, const MomentsTail &tail, Sums *scratch)
 {
     __shared__ bool is_last;
     __syncthreads();  // scratch may have been used before
-    Moments m = block_merge(mine, scratch);
+    const Sums blk = block_reduce_sums(mine, scratch);
     if (threadIdx.x == 0) {
-        tail.partials[blockIdx.x] = m;
+        tail.partials[blockIdx.x] = blk;
         __threadfence();
         const unsigned t = atomicAdd(tail.ticket, 1u);
         is_last = (t == gridDim.x - 1);
@@ -180,24 +181,31 @@ __device__ __forceinline__ void moments_tail(Moments mine, const MomentsTail &ta
     __syncthreads();
     if (!is_last) return;
     __threadfence();
-    Moments acc;
-    acc.n = 0.0; acc.mean = 0.0; acc.m2 = 0.0;
-    // contiguous slices per thread keep the merge order = CTA index order
+    // contiguous slices per thread keep the summation order = CTA index order
     const unsigned n = gridDim.x;
     const unsigned per = (n + blockDim.x - 1) / blockDim.x;
     const unsigned lo = threadIdx.x * per;
+    Sums acc;
+    acc.n = 0.0; acc.s1 = 0.0; acc.s2 = 0.0; acc.piv = 0.0;
     for (unsigned i = lo; i < lo + per && i < n; ++i) {
-        const volatile Moments *vp = tail.partials + i;
-        Moments q;
-        q.n = vp->n; q.mean = vp->mean; q.m2 = vp->m2;
-        acc = merge(acc, q);
+        const volatile Sums *vp = tail.partials + i;
+        Sums q;
+        q.n = vp->n; q.s1 = vp->s1; q.s2 = vp->s2; q.piv = vp->piv;
+        if (q.n > 0.0) {
+            if (acc.n == 0.0) acc = q;
+            else {
+                q = rebase(q, acc.piv);
+                acc.n += q.n; acc.s1 += q.s1; acc.s2 += q.s2;
+            }
+        }
     }
     __syncthreads();
-    acc = block_merge(acc, scratch);
+    acc = block_reduce_sums(acc, scratch);
     if (threadIdx.x == 0) {
-        tail.moments_out[0] = acc.n;
-        tail.moments_out[1] = acc.mean;
-        tail.moments_out[2] = acc.m2;
+        const Moments m = to_moments(acc);
+        tail.moments_out[0] = m.n;
+        tail.moments_out[1] = m.mean;
+        tail.moments_out[2] = m.m2;
         *tail.ticket = 0u;  // ready for the next launch
     }
 }

@@ -14,7 +14,7 @@ __global__ void __launch_bounds__(256)
 batch_moments_kernel(const float *__restrict__ x, int64_t ld_x, int64_t rows, int64_t cols,
                      const uint8_t *__restrict__ valid, int64_t ld_v, MomentsTail tail)
 {
-    __shared__ Moments scratch[32];
+    __shared__ Sums scratch[32];
     PivotAcc acc;
     acc.init();
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -55,7 +55,7 @@ batch_moments_kernel(const float *__restrict__ x, int64_t ld_x, int64_t rows, in
             if (!MASKED || valid[r * ld_v + c]) acc.add(x[r * ld_x + c]);
         }
     }
-    moments_tail(acc.finish(), tail, scratch);
+    moments_tail(acc.sums(), tail, scratch);
 }
 
 // ---------------------------------------------------------------------------------

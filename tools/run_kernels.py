@@ -24,14 +24,25 @@ def timed(fn, reps, flush=None, inner=1):
     resolution on this box is ~2 us); inner > 1: `inner` back-to-back launches per event pair
     (callers rotate buffer sets larger than L2 through `i`)."""
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
-    k = 0
+    graph = None
+    if inner > 1:  # capture `inner` launches into one CUDA graph: no host overhead between kernels
+        for k in range(inner):
+            fn(k)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            for k in range(inner):
+                fn(k)
+        graph.replay()
+        torch.cuda.synchronize()
     for i in range(reps):
         if flush is not None and inner == 1:
             flush.zero_()
         ev[i][0].record()
-        for _ in range(inner):
-            fn(k)
-            k += 1
+        if graph is not None:
+            graph.replay()
+        else:
+            fn(i)
         ev[i][1].record()
     torch.cuda.synchronize()
     return [a.elapsed_time(b) * 1e3 / inner for a, b in ev]
@@ -58,7 +69,7 @@ def main():
     rng = np.random.default_rng(0)
     flush = torch.empty(256 * 2**20, dtype=torch.uint8, device=dev)  # > L2
     T, B = args.T, args.B
-    if args.what in ("gae", "normadv", "past"):
+    if args.what in ("gae", "normadv", "past", "gae_stats", "step", "chain"):
         n_sets = 1 if args.inner == 1 else max(2, int(np.ceil(2.5 * 126 * 2**20 / (17 * T * B))))
         trees = []
         for _ in range(n_sets):
@@ -71,6 +82,17 @@ def main():
         if args.what == "gae":
             tf = EstimateAdvantage(0.99, args.lam, algo=args.algo)
             nbytes = 17 * T * B
+        elif args.what in ("gae_stats", "step", "chain"):
+            from parllel_b200.transforms import ClipRewards, FusedBatchTransforms
+            if args.what == "chain":
+                lst = [NormalizeRewards(tree, 0.99), ClipRewards(-5, 5), EstimateAdvantage(0.99, args.lam), NormalizeAdvantage(tree)]
+                nbytes = 25 * T * B
+            else:
+                lst = [EstimateAdvantage(0.99, args.lam), NormalizeAdvantage(tree)]
+                nbytes = 17 * T * B
+            fz = FusedBatchTransforms(lst, use_cuda_graph=False)
+            ph = _lib.PHASE_B if args.what == "gae_stats" else _lib.PHASE_ALL
+            tf = lambda tr: fz(tr, phases=ph)
         elif args.what == "normadv":
             for tr in trees:
                 EstimateAdvantage(0.99, args.lam, algo=args.algo)(tr)
