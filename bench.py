@@ -123,7 +123,7 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- CPU arm
-def cpu_reference_arm(steps: int, warmup: int, budget_s: float, threads: int):
+def cpu_reference_arm(steps: int, warmup: int, budget_s: float, threads: int, n_shards: int = 1):
     """The reference algorithm on host cores: oracle C scans (column blocks over a thread pool; the
     numba original is single-threaded) + numpy float32 reductions, same step as the GPU arm."""
     from concurrent.futures import ThreadPoolExecutor
@@ -131,10 +131,11 @@ def cpu_reference_arm(steps: int, warmup: int, budget_s: float, threads: int):
     from oracle import oracle as O
 
     O.lib()
-    batch = synth_batch(1)
+    B_all = B_ENVS * n_shards  # the whole job's batch: every rank's shard, processed on the host
+    batch = synth_batch(1, B=B_all)
     adv = np.empty_like(batch["value"])
     ret = np.empty_like(batch["value"])
-    blocks = np.array_split(np.arange(B_ENVS), threads)
+    blocks = np.array_split(np.arange(B_all), max(threads, 1))
     pool = ThreadPoolExecutor(threads)
 
     def scan_block(cols):
@@ -158,10 +159,16 @@ def cpu_reference_arm(steps: int, warmup: int, budget_s: float, threads: int):
             break
     pool.shutdown()
     per_step = sum(times) / len(times)
-    return {"value": T_STEPS * B_ENVS / per_step, "ms_per_step": per_step * 1e3, "steps": len(times)}
+    return {"value": T_STEPS * B_all / per_step, "ms_per_step": per_step * 1e3, "steps": len(times)}
 
 
 # ----------------------------------------------------------------------------- main
+def _debug(msg):
+    if os.environ.get("PLB_BENCH_DEBUG"):
+        sys.stderr.write(f"[bench rank {os.environ.get('RANK', '0')} t={time.perf_counter():.2f}] {msg}\n")
+        sys.stderr.flush()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -186,13 +193,14 @@ def main():
         if rank != 0:
             return
         threads = min(cores, 32)
-        res = cpu_reference_arm(args.steps, warmup, budget_s=60.0, threads=threads)
+        res = cpu_reference_arm(args.steps, warmup, budget_s=60.0, threads=threads, n_shards=max(args.gpus, 1))
         line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
                 "steps": res["steps"], "warmup": warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64 step / f32 store", "data": "synthetic",
                 "config": config,
                 "cpu_baseline": {"value": res["value"], "unit": UNIT, "cores": threads, "kind": "port",
-                                 "sample": f"{res['steps']} full C1 steps (oracle C scans over {threads} threads + numpy reductions)"},
+                                 "sample": f"{res['steps']} steps over the whole job's batch [T={T_STEPS}, B={B_ENVS * max(args.gpus, 1)}] "
+                                           f"(oracle C scans over {threads} threads + numpy reductions)"},
                 "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
@@ -230,6 +238,7 @@ def main():
     def step(i):
         fused(sets[i % n_sets])
 
+    _debug("buffers ready")
     for i in range(max(warmup, 3 * n_sets)):  # every buffer set: eager pass, capture pass, replay pass
         step(i)
     torch.cuda.synchronize()
@@ -237,6 +246,7 @@ def main():
         dist.barrier()
     torch.cuda.synchronize()
 
+    _debug("warm-up done")
     stream = torch.cuda.current_stream(dev)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clocks:
@@ -246,6 +256,7 @@ def main():
         ev1.record(stream)
         torch.cuda.synchronize()
         elapsed_ms = ev0.elapsed_time(ev1)
+        _debug("timed region done")
 
         # dominant kernel alone (phase B of the same chain = the GAE scan with fused advantage moments):
         # one launch per buffer set captured into a CUDA graph, replayed until `steps` launches have run
@@ -269,11 +280,10 @@ def main():
         kernel_launches = n_replays * n_sets
         gae_us = k0.elapsed_time(k1) * 1e3 / kernel_launches
 
-        t_end = time.perf_counter() + 0.5  # keep the GPU under the same load for a few clock samples
-        j = 0
-        while time.perf_counter() < t_end:
+        # keep the GPU under the same load for a few clock samples (a FIXED number of extra steps: with
+        # N > 1 every step holds a collective, so all ranks must run the same count)
+        for j in range(min(max(args.steps, 2000), 20000)):
             step(j)
-            j += 1
         torch.cuda.synchronize()
     if distributed:
         dist.barrier()
@@ -283,6 +293,7 @@ def main():
     transitions = T_STEPS * B_ENVS * world * args.steps
     value = transitions / (elapsed_ms * 1e-3)
 
+    _debug("kernel loop + clock hold done")
     # ---- e2e: the same public API on HOST (pinned numpy) leaves: H2D + kernels + D2H every step ----
     e2e_steps = args.e2e_steps or min(args.steps, 40)
     host_sets = [PinnedBatch(synth_batch(7000 + 10 * rank + i)) for i in range(2)]

@@ -28,9 +28,10 @@ def column_shard(B: int, world_size: int, rank: int) -> slice:
 def all_gather_moments(local: torch.Tensor, group=None) -> torch.Tensor:
     """All-gather a rank's float64 moments; returns ``[world, *local.shape]`` in rank order."""
     world = dist.get_world_size(group)
-    out = torch.empty((world,) + tuple(local.shape), dtype=local.dtype, device=local.device)
-    dist.all_gather_into_tensor(out, local.contiguous(), group=group)
-    return out
+    flat = local.contiguous().reshape(-1)
+    out = torch.empty(world * flat.numel(), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, flat, group=group)  # flat in / flat out works for NCCL and gloo
+    return out.reshape((world,) + tuple(local.shape))
 
 
 def merge_gathered_moments(gathered: torch.Tensor, n_cols: int, layout: int, out: torch.Tensor) -> None:
@@ -54,3 +55,16 @@ class ShardedNormalizeAdvantage(NormalizeAdvantage):
         local = moments[: 3 * inner]
         gathered = all_gather_moments(local, self.group)
         merge_gathered_moments(gathered, inner, 0, local)
+
+
+def shard_statistics(transform, group=None):
+    """Switch a statistics-carrying transform (``NormalizeRewards``, ``NormalizeObservations``) to
+    B-sharded operation: every update all-gathers the per-rank batch moments over ``group`` and merges
+    them in rank order, so all ranks hold bit-identical running statistics of the WHOLE batch.
+    Returns the transform for chaining."""
+    for name in ("return_statistics", "obs_statistics"):
+        stats = getattr(transform, name, None)
+        if stats is not None:
+            stats.sharded = True
+            stats.group = group
+    return transform

@@ -63,6 +63,17 @@ class NormalizeObservations(Transform):
         return observation
 
     def _step(self, obs: torch.Tensor, valid, device) -> None:
+        if self.obs_statistics.sharded:
+            # B-sharded: local column moments -> all-gather + merge -> update state -> local normalise
+            self.obs_statistics.update(obs, valid=None if valid is None else valid.reshape(-1).contiguous())
+            B = obs.shape[0]
+            x = obs.reshape(B, -1)
+            ptr, ld, cols = rows_2d(x)
+            stats = self.obs_statistics
+            _lib.check(_lib.load().plb_normalize_columns_f32(ptr, ld, B, cols, stats.mean_tensor.data_ptr(),
+                                                             stats.var_tensor.data_ptr(), EPSILON, stream_ptr(device)),
+                       "plb_normalize_columns_f32")
+            return
         lib = _lib.load()
         B = obs.shape[0]
         F = int(np.prod(self.obs_shape, dtype=np.int64)) if self.obs_shape else 1

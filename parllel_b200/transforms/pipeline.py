@@ -174,7 +174,7 @@ class FusedBatchTransforms(Transform):
 
         def enqueue():
             s = stream_ptr(dev)
-            if self._distributed():
+            if self._distributed() and phases == _lib.PHASE_ALL:
                 _lib.check(lib.plb_batch_pipeline_f32(ctypes.byref(d), _lib.PHASE_A, s), "fused transforms (A)")
                 if nr is not None:
                     self._exchange(self._moments[0:3])
@@ -190,7 +190,8 @@ class FusedBatchTransforms(Transform):
                 if nr._carry_done is not None:
                     nr._carry_done.copy_(done[T - 1])
 
-        graphable = (self.use_cuda_graph and not st.staged and not self._distributed())
+        # the NCCL all-gathers of the sharded chain are captured into the graph as well
+        graphable = self.use_cuda_graph and not st.staged
         if not graphable:
             enqueue()
         else:

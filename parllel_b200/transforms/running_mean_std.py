@@ -26,6 +26,10 @@ class RunningMeanStd:
         # scratch for batch moments: scalar -> (count, mean, M2); per column -> count[1], mean[n], m2[n]
         self._moments = torch.zeros(3 if n == 1 else 1 + 2 * n, dtype=torch.float64, device=self.device)
         self._ws = None
+        # B-sharded operation (parllel_b200.distributed.shard_statistics): batch moments are all-gathered
+        # over this process group and merged in rank order before they update the running state
+        self.sharded = False
+        self.group = None
 
     # -- numpy views of the state (D2H copies) ------------------------------------------
     @property
@@ -71,6 +75,8 @@ class RunningMeanStd:
             _lib.check(lib.plb_batch_moments_f32(ptr, ld, rows, cols, vptr, vld, self._moments.data_ptr(),
                                                  ws.data_ptr(), ws.numel(), s), "plb_batch_moments_f32")
             m = self._moments
+            if self.sharded:
+                self._exchange(layout=0)
             _lib.check(lib.plb_update_from_moments_f64(m.data_ptr(), m.data_ptr() + 8, m.data_ptr() + 16,
                                                        self.mean_tensor.data_ptr(), self.var_tensor.data_ptr(),
                                                        self.count_tensor.data_ptr(), 1, flags, s),
@@ -87,6 +93,13 @@ class RunningMeanStd:
             cnt, mean, m2 = m.data_ptr(), m.data_ptr() + 8, m.data_ptr() + 8 * (1 + self._n)
             _lib.check(lib.plb_column_moments_f32(ptr, ld, rows, cols, vptr, cnt, mean, m2,
                                                   ws.data_ptr(), ws.numel(), s), "plb_column_moments_f32")
+            if self.sharded:
+                self._exchange(layout=1)
             _lib.check(lib.plb_update_from_moments_f64(cnt, mean, m2, self.mean_tensor.data_ptr(),
                                                        self.var_tensor.data_ptr(), self.count_tensor.data_ptr(),
                                                        self._n, flags, s), "plb_update_from_moments_f64")
+
+    def _exchange(self, layout: int) -> None:
+        from ..distributed import all_gather_moments, merge_gathered_moments
+        gathered = all_gather_moments(self._moments, self.group)
+        merge_gathered_moments(gathered, 1 if layout == 0 else self._n, layout, self._moments)
