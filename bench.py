@@ -319,9 +319,29 @@ def main():
     h2d = T_STEPS * B_ENVS * 9 + B_ENVS * 4   # reward, value, done, bootstrap_value
     d2h = T_STEPS * B_ENVS * 8                # advantage, return_
 
-    if rank != 0:
-        if distributed:
+    def shutdown():
+        """Leave cleanly: drop captured graphs (they pin NCCL work) before the process group; a watchdog
+        forces the exit if NCCL teardown stalls, so the harness never waits on a finished benchmark."""
+        sys.stdout.flush()
+        if not distributed:
+            return
+        killer = threading.Timer(20.0, lambda: os._exit(0))
+        killer.daemon = True
+        killer.start()
+        try:
+            for obj in (fused, e2e_fused):
+                obj._graphs.clear()
+                obj._bound.clear()
+            import gc
+            gc.collect()
+            torch.cuda.synchronize()
+            dist.barrier()
             dist.destroy_process_group()
+        finally:
+            killer.cancel()
+
+    if rank != 0:
+        shutdown()
         return
 
     peak, peak_src = measured_peak()
@@ -349,8 +369,7 @@ def main():
                                 "sample": f"{res['steps']} full C1 steps, single thread like the numba original "
                                           f"(oracle C scans + numpy reductions); host has {cores} cores"}
     print(json.dumps(line))
-    if distributed:
-        dist.destroy_process_group()
+    shutdown()
 
 
 if __name__ == "__main__":
