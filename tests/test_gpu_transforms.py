@@ -125,6 +125,41 @@ def test_fused_batch_transforms_match_reference(golden, name, leaves, graph):
         np.testing.assert_allclose([st.mean, st.var, st.count], g[f"b{it}_out_stats"], rtol=2e-6)
 
 
+@pytest.mark.parametrize("name", ["pipeline_c0", "pipeline_lambda1"])
+def test_host_batch_pipeline_overlapped_submits(golden, name):
+    """Host trees through HostBatchPipeline: batch i+1 is submitted before batch i is waited on."""
+    from parllel_b200 import ArrayDict
+    from parllel_b200.host_pipeline import HostBatchPipeline
+    from parllel_b200.transforms import (ClipRewards, EstimateAdvantage, FusedBatchTransforms, NormalizeAdvantage,
+                                         NormalizeRewards)
+    g = golden(name)
+    T, B, p_done, n_batches, with_valid, lam, clip_lo, clip_hi, init_count = g["meta"]
+    T, B, n_batches = int(T), int(B), int(n_batches)
+
+    def host_tree(it):
+        return ArrayDict({
+            "reward": g[f"b{it}_in_reward"].copy(), "done": g[f"b{it}_in_done"].copy(),
+            "agent_info": {"value": g[f"b{it}_in_value"].copy()},
+            "bootstrap_value": g[f"b{it}_in_bootstrap_value"].copy(),
+            "advantage": np.zeros((T, B), np.float32), "return_": np.zeros((T, B), np.float32),
+            "past_return": np.zeros((T, B), np.float32)})
+
+    trees = [host_tree(it) for it in range(n_batches)]
+    fused = FusedBatchTransforms([
+        NormalizeRewards(trees[0], discount=0.99, initial_count=None if init_count < 0 else init_count),
+        ClipRewards(reward_min=clip_lo, reward_max=clip_hi),
+        EstimateAdvantage(discount=0.99, gae_lambda=lam),
+        NormalizeAdvantage(trees[0]),
+    ])
+    pipe = HostBatchPipeline(fused)
+    handles = [pipe.submit(t) for t in trees]  # all in flight at once (more batches than slots)
+    for it, h in enumerate(handles):
+        out = h.wait()
+        assert out is trees[it]
+        for k in ("past_return", "reward", "return_", "advantage"):
+            assert_within_tolerance(out[k], g[f"b{it}_out_{k}"], what=f"{name} batch {it} {k}")
+
+
 def test_fused_subsets_and_order_errors():
     from parllel_b200.transforms import ClipRewards, EstimateAdvantage, FusedBatchTransforms, NormalizeAdvantage
     with pytest.raises(ValueError):
