@@ -143,7 +143,7 @@ normalize_columns_kernel(float *__restrict__ x, int64_t ld_x, int64_t rows, int6
 #pragma unroll
     for (int k = 0; k < VEC; ++k) {
         mu[k] = mean[c0 + k];
-        den[k] = sqrt(__dadd_rn(var[c0 + k], eps));
+        den[k] = 1.0 / sqrt(__dadd_rn(var[c0 + k], eps));  // multiplied below: <= 1 ulp(float64) from the division
     }
     const int64_t r_lo = (int64_t)blockIdx.y * rows_per_split;
     const int64_t r_hi = (r_lo + rows_per_split < rows) ? r_lo + rows_per_split : rows;
@@ -166,7 +166,7 @@ normalize_columns_kernel(float *__restrict__ x, int64_t ld_x, int64_t rows, int6
             if (r + u < r_hi) {
 #pragma unroll
                 for (int k = 0; k < VEC; ++k)
-                    v[u][k] = __double2float_rn(__ddiv_rn(__dsub_rn((double)v[u][k], mu[k]), den[k]));
+                    v[u][k] = __double2float_rn(__dmul_rn(__dsub_rn((double)v[u][k], mu[k]), den[k]));
                 if (VEC == 4) {
                     float4 q;
                     q.x = v[u][0]; q.y = v[u][1 % VEC]; q.z = v[u][2 % VEC]; q.w = v[u][3 % VEC];
@@ -295,6 +295,18 @@ int plb_normalize_observations_step_f32(float *obs, int64_t ld_obs, int64_t rows
                 "observation step needs %zu workspace bytes, got %zu", need, workspace_bytes);
     double *batch_count = reinterpret_cast<double *>(workspace);
     Moments *partials = reinterpret_cast<Moments *>(reinterpret_cast<unsigned char *>(workspace) + 64);
+
+    // single pass over HBM when a [rows x 16 columns] slab fits in shared memory
+    {
+        const int rc1 = obs_step_single_pass(obs, ld_obs, rows, cols, row_valid, mean, var, count, batch_count,
+                                             eps, flags, stream);
+        if (rc1 == PLB_OK) {
+            bump_count_kernel<<<1, 1, 0, stream>>>(count, batch_count);
+            PLB_LAUNCH_CHECK();
+            return PLB_OK;
+        }
+        if (rc1 != PLB_ERR_UNSUPPORTED) return rc1;
+    }
 
     const int splits = column_moments_splits(rows, cols);
     int rc = column_moments_partial(obs, ld_obs, rows, cols, row_valid, partials, splits, stream);

@@ -58,6 +58,9 @@ int column_moments_partial(const float *x, int64_t ld_x, int64_t rows, int64_t c
 int column_moments(const float *x, int64_t ld_x, int64_t rows, int64_t cols, const uint8_t *row_valid,
                    double *count_out, double *mean_out, double *m2_out,
                    void *workspace, size_t workspace_bytes, cudaStream_t stream);
+int obs_step_single_pass(float *x, int64_t ld, int64_t rows, int64_t cols, const uint8_t *row_valid,
+                         double *mean, double *var, const double *count, double *batch_count_out,
+                         double eps, int flags, cudaStream_t stream);
 int make_tensor_map_2d(CUtensorMap *tm, const void *base, int elem_bytes, int64_t rows, int64_t cols,
                        int64_t ld_elems, int box_rows, int box_cols);
 
