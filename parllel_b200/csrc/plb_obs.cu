@@ -19,10 +19,11 @@
 namespace plb {
 namespace obs {
 
-constexpr int FC = 16;          // columns per slab (64-byte row segments)
+constexpr int FC = 16;           // columns per slab (64-byte row segments)
 constexpr int THREADS = 256;
 constexpr int GROUPS = THREADS / FC;  // 16 row groups; thread (g, c) takes rows g, g+16, g+32, ...
-constexpr int BOX_ROWS = 256;   // rows per TMA box (box dimensions are limited to 256)
+constexpr int BOX_ROWS = 256;    // rows per TMA box (box dimensions are limited to 256)
+constexpr int MAX_BUFS = 4;
 
 struct Params {
     int64_t rows, cols;
@@ -34,56 +35,107 @@ struct Params {
     int flags;
     int n_slabs;
     int n_boxes;              // ceil(rows / BOX_ROWS)
+    int n_bufs;               // slab buffers in the shared-memory ring (>= 1)
+    int slab_floats;          // floats per slab buffer = n_boxes * BOX_ROWS * FC
 };
 
 __global__ void __launch_bounds__(THREADS)
 obs_step_kernel(const __grid_constant__ CUtensorMap tm, const Params p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    float (*slab)[FC] = reinterpret_cast<float (*)[FC]>(smem_raw);  // [n_boxes * BOX_ROWS][FC]
-    __shared__ unsigned long long bar;
+    float *ring = reinterpret_cast<float *>(smem_raw);  // n_bufs x [n_boxes * BOX_ROWS][FC]
+    __shared__ unsigned long long full[MAX_BUFS];
     __shared__ Sums part[GROUPS][FC];
     __shared__ double col_mean[FC], col_inv[FC];
 
     const int c = threadIdx.x % FC, g = threadIdx.x / FC;
-    const int64_t rows = p.rows;
-    const uint32_t box_bytes = BOX_ROWS * FC * sizeof(float);
+    const int nrows = (int)p.rows;
+    const int n_bufs = p.n_bufs;
+    const uint32_t slab_tx = (uint32_t)p.slab_floats * sizeof(float);
+    const int my_n = (p.n_slabs - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+    auto load_slab = [&](int j) {  // thread 0 only
+        const int buf = j % n_bufs;
+        const int c0 = ((int)blockIdx.x + j * (int)gridDim.x) * FC;
+        float *dst = ring + (size_t)buf * p.slab_floats;
+        mbar_arrive_expect_tx(&full[buf], slab_tx);
+        for (int bx = 0; bx < p.n_boxes; ++bx) tma_load_2d(dst + (size_t)bx * BOX_ROWS * FC, &tm, c0, bx * BOX_ROWS, &full[buf]);
+    };
 
     if (threadIdx.x == 0) {
-        mbar_init(&bar, 1);
+        for (int k = 0; k < n_bufs; ++k) mbar_init(&full[k], 1);
         fence_proxy_async_smem();
         tma_prefetch_desc(&tm);
     }
     __syncthreads();
+    const int lead = n_bufs > 1 ? n_bufs - 1 : 1;  // slabs requested ahead of the one being processed
+    if (threadIdx.x == 0)
+        for (int j = 0; j < lead && j < my_n; ++j) load_slab(j);
 
-    uint32_t phase = 0;
-    for (int s = blockIdx.x; s < p.n_slabs; s += gridDim.x) {
+    const double cnt = p.count[0];
+    for (int i = 0; i < my_n; ++i) {
+        const int buf = i % n_bufs;
+        const uint32_t parity = (uint32_t)((i / n_bufs) & 1);
+        const int s = (int)blockIdx.x + i * (int)gridDim.x;
         const int c0 = s * FC;
-        if (threadIdx.x == 0) {
-            mbar_arrive_expect_tx(&bar, box_bytes * p.n_boxes);
-            for (int b = 0; b < p.n_boxes; ++b) tma_load_2d(&slab[b * BOX_ROWS][0], &tm, c0, b * BOX_ROWS, &bar);
-        }
+        float (*slab)[FC] = reinterpret_cast<float (*)[FC]>(ring + (size_t)buf * p.slab_floats);
         const bool col_ok = (int64_t)c0 + c < p.cols;
-        const double old_mean = col_ok ? p.mean[c0 + c] : 0.0;   // overlaps the load
-        const double old_var = col_ok ? p.var[c0 + c] : 1.0;
-        const double cnt = p.count[0];
-        mbar_wait(&bar, phase);
-        phase ^= 1u;
+        const double old_mean = (g == 0 && col_ok) ? p.mean[c0 + c] : 0.0;   // overlaps the load
+        const double old_var = (g == 0 && col_ok) ? p.var[c0 + c] : 1.0;
+        mbar_wait(&full[buf], parity);
 
-        // ---- batch moments of this slab: rows g, g+16, ... of column c -----------------
-        PivotAcc acc;
-        acc.init();
+        // ---- batch moments of this slab: rows g, g+GROUPS, ... of column c --------------
+        // float32 pivot-shifted sums over runs of 16 rows, folded into float64 per run: one
+        // conversion pair per 16 elements instead of one per element (F2F is a quarter-rate pipe)
+        const float piv = (g < nrows) ? slab[g][c] : 0.f;  // pivot: any value of the column's magnitude
+        double S1 = 0.0, S2 = 0.0;
+        unsigned n_acc = 0;
         if (p.row_valid == nullptr) {
-#pragma unroll 4
-            for (int64_t r = g; r < rows; r += GROUPS) acc.add(slab[r][c]);
+            int r0 = g;
+            for (; r0 + 15 * GROUPS < nrows; r0 += GROUPS * 16) {  // full runs: no predicates
+                float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    const float d = slab[r0 + k * GROUPS][c] - piv;
+                    s1 += d;
+                    s2 = fmaf(d, d, s2);
+                }
+                S1 += (double)s1;
+                S2 += (double)s2;
+                n_acc += 16;
+            }
+            float s1 = 0.f, s2 = 0.f;
+            for (int r = r0; r < nrows; r += GROUPS) {
+                const float d = slab[r][c] - piv;
+                s1 += d;
+                s2 = fmaf(d, d, s2);
+                ++n_acc;
+            }
+            S1 += (double)s1;
+            S2 += (double)s2;
         } else {
-            for (int64_t r = g; r < rows; r += GROUPS)
-                if (p.row_valid[r] != 0) acc.add(slab[r][c]);
+            for (int r0 = g; r0 < nrows; r0 += GROUPS * 16) {
+                float s1 = 0.f, s2 = 0.f;
+#pragma unroll 4
+                for (int k = 0; k < 16; ++k) {
+                    const int r = r0 + k * GROUPS;
+                    if (r < nrows && p.row_valid[r] != 0) {
+                        const float d = slab[r][c] - piv;
+                        s1 += d;
+                        s2 = fmaf(d, d, s2);
+                        ++n_acc;
+                    }
+                }
+                S1 += (double)s1;
+                S2 += (double)s2;
+            }
         }
-        part[g][c] = acc.sums();
+        Sums mine;
+        mine.n = (double)n_acc; mine.s1 = S1; mine.s2 = S2; mine.piv = (double)piv;
+        part[g][c] = mine;
         __syncthreads();
         if (g == 0) {
-            // division-free merge of the 16 row groups (fixed order), then the reference's update
+            // division-free merge of the row groups (fixed order), then the reference's update
             Sums tot = part[0][c];
             for (int k = 1; k < GROUPS; ++k) {
                 Sums q = part[k][c];
@@ -122,19 +174,32 @@ obs_step_kernel(const __grid_constant__ CUtensorMap tm, const Params p)
         }
         __syncthreads();
 
-        // ---- normalise the slab in place (float64 arithmetic, one rounding to float32) --
+        // ---- normalise the slab in place --------------------------------------------------
+        // y = (x - mean) * inv with mean and inv = 1/sqrt(var+eps) carried as float32 hi+lo pairs:
+        // (x - mean_hi) is exact or correctly rounded, the lo parts restore the float64 constants;
+        // |y - y_float64| <= ~1.5 ulp(float32) of y, without any float64 conversion per element.
         const double mu = col_mean[c], inv = col_inv[c];
-#pragma unroll 4
-        for (int64_t r = g; r < rows; r += GROUPS)
-            slab[r][c] = __double2float_rn(((double)slab[r][c] - mu) * inv);
+        const float mu_hi = __double2float_rn(mu), mu_lo = __double2float_rn(mu - (double)mu_hi);
+        const float inv_hi = __double2float_rn(inv), inv_lo = __double2float_rn(inv - (double)inv_hi);
+#pragma unroll 8
+        for (int r = g; r < nrows; r += GROUPS) {
+            const float d = (slab[r][c] - mu_hi) - mu_lo;
+            slab[r][c] = fmaf(d, inv_hi, d * inv_lo);
+        }
         fence_proxy_async_smem();
         __syncthreads();
         if (threadIdx.x == 0) {
-            for (int b = 0; b < p.n_boxes; ++b) tma_store_2d(&tm, &slab[b * BOX_ROWS][0], c0, b * BOX_ROWS);
+            for (int bx = 0; bx < p.n_boxes; ++bx) tma_store_2d(&tm, &slab[bx * BOX_ROWS][0], c0, bx * BOX_ROWS);
             tma_store_commit();
-            tma_store_wait_read<0>();  // the slab buffer is reused by the next TMA load
+            // request the slab `lead` ahead: it lands in the buffer whose store was committed one
+            // iteration ago (ring of >= 2 buffers) or in this very buffer (single buffer)
+            const int j = i + lead;
+            if (j < my_n) {
+                if (n_bufs > 1) tma_store_wait_read<1>();
+                else tma_store_wait_read<0>();
+                load_slab(j);
+            }
         }
-        __syncthreads();
     }
     if (threadIdx.x == 0) tma_store_wait<0>();
 }
@@ -157,7 +222,8 @@ int obs_step_single_pass(float *x, int64_t ld, int64_t rows, int64_t cols, const
         PLB_CUDA(cudaFuncGetAttributes(&attr, obs_step_kernel));
         static_bytes = attr.sharedSizeBytes;
     }
-    if (slab_bytes + static_bytes > 227 * 1024) return PLB_ERR_UNSUPPORTED;
+    const size_t avail = 227 * 1024 - static_bytes;
+    if (slab_bytes > avail) return PLB_ERR_UNSUPPORTED;
     CUtensorMap tm;
     int rc = make_tensor_map_2d(&tm, x, 4, rows, cols, ld, BOX_ROWS, FC);
     if (rc) return rc;
@@ -171,17 +237,26 @@ int obs_step_single_pass(float *x, int64_t ld, int64_t rows, int64_t cols, const
     p.eps = eps; p.flags = flags;
     p.n_slabs = (int)ceil_div(cols, FC);
     p.n_boxes = n_boxes;
+    p.slab_floats = n_boxes * BOX_ROWS * FC;
+    // Measured at C2 (B = 1024, 64 KB slabs): three independent single-buffer CTAs per SM (52 us) beat
+    // one persistent CTA per SM with a 3-slab ring (66 us) -- with 64-byte rows the TMA unit is the
+    // limiter (tools/microbench/tma_width.cu: 4.4 TB/s at 64 B, 5.3 at 128 B, 5.9 at 256 B per row
+    // request) and independent CTAs keep more row requests in flight.  The ring is used only when
+    // slabs are small enough that several fit next to several CTAs.
     int ctas_per_sm = (int)((228 * 1024) / (slab_bytes + static_bytes + 1024));
     if (ctas_per_sm < 1) ctas_per_sm = 1;
-    if (ctas_per_sm > 8) ctas_per_sm = 8;
+    if (ctas_per_sm > 4) ctas_per_sm = 4;
+    int n_bufs = (int)(((228 * 1024) / ctas_per_sm - static_bytes - 1024) / slab_bytes);
+    if (n_bufs > MAX_BUFS) n_bufs = MAX_BUFS;
+    if (n_bufs < 1) n_bufs = 1;
+    p.n_bufs = n_bufs;
     const int grid = p.n_slabs < sms * ctas_per_sm ? p.n_slabs : sms * ctas_per_sm;
-    static thread_local size_t configured = 0;
-    if (slab_bytes > configured) {
-        PLB_CUDA(cudaFuncSetAttribute(obs_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)(227 * 1024 - static_bytes)));
-        configured = 227 * 1024;
+    static thread_local bool configured = false;
+    if (!configured) {
+        PLB_CUDA(cudaFuncSetAttribute(obs_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)avail));
+        configured = true;
     }
-    obs_step_kernel<<<grid, THREADS, slab_bytes, stream>>>(tm, p);
+    obs_step_kernel<<<grid, THREADS, slab_bytes * n_bufs, stream>>>(tm, p);
     PLB_LAUNCH_CHECK();
     return PLB_OK;
 }
