@@ -165,6 +165,20 @@ class ReplayBuffer:
         batch = self.batch_transform(batch)
         return batch
 
+    def sample_batches(self, k: int) -> ArrayDict:
+        """``k`` consecutive ``sample_batch()`` calls fused into ONE gather launch.  The index
+        stream is exactly that of ``k`` sequential calls (T draw then B draw per minibatch), which is
+        legal whenever the ring is not written in between -- SAC draws ``updates_per_optimize``
+        minibatches per iteration that way (torch/algos/sac.py:112-115).  Leaves come back as
+        ``[k, batch, *feat]``; ``batch_transform`` is applied to the stacked tree."""
+        idx = [self.sample_indices() for _ in range(k)]
+        T_all = np.concatenate([t for t, _ in idx])
+        B_all = np.concatenate([b for _, b in idx])
+        flat = self.gather(T_all, B_all)
+        n = self.batch_size
+        stacked = flat.apply(lambda leaf: leaf.reshape((k, n) + tuple(leaf.shape[1:])))
+        return self.batch_transform(stacked)
+
     def batches(self) -> Iterator[ArrayDict]:
         while True:
             yield self.sample_batch()

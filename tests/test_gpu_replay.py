@@ -122,3 +122,79 @@ def test_gather_odd_row_sizes_and_alignments():
     got = rb.gather(t_idx, b_idx)
     for k, v in dev.items():
         assert torch.equal(got[k].cpu(), v.cpu()[torch.from_numpy(t_idx), torch.from_numpy(b_idx)]), k
+
+
+def test_k_fused_sampling_equals_sequential_calls(golden):
+    """sample_batches(k) = k sample_batch() calls: same index stream, same bytes, one launch."""
+    from parllel_b200 import BatchSpec
+    from parllel_b200.replays import ReplayBuffer
+    g = golden("replay")
+    tree, T, B, size_T = _ring_tree(g, "cuda")
+    a = ReplayBuffer(tree, BatchSpec(T, B), size_T=size_T, replay_batch_size=33, oldest_n_samples_invalid=1)
+    b = ReplayBuffer(tree, BatchSpec(T, B), size_T=size_T, replay_batch_size=33, oldest_n_samples_invalid=1)
+    for rb in (a, b):
+        rb._full, rb._cursor = True, 24
+        rb.seed(11)
+    fused = a.sample_batches(5)
+    for i in range(5):
+        single = b.sample_batch()
+        for k in single:
+            assert torch.equal(fused[k][i], single[k]), (i, k)
+    # the generators stay aligned afterwards
+    assert np.array_equal(a.sample_indices()[0], b.sample_indices()[0])
+
+
+@pytest.mark.parametrize("residency", ["cuda", "host"])
+def test_batched_dataloader_matches_reference_golden(golden, residency):
+    from parllel_b200 import ArrayDict, BatchSpec
+    from parllel_b200.replays import BatchedDataLoader
+    g = golden("dataloader")
+    T, B = (int(x) for x in g["meta"])
+    leaves = {k: torch.from_numpy(g[f"in_{k}"]) for k in ("observation", "advantage", "return_", "action")}
+    tt, bb = np.meshgrid(np.arange(T), np.arange(B), indexing="ij")
+    leaves["t_index"] = torch.from_numpy(tt.copy())
+    leaves["b_index"] = torch.from_numpy(bb.copy())
+    if residency == "cuda":
+        leaves = {k: v.cuda() for k, v in leaves.items()}
+    for name, n_batches, drop_last, shuffle in [("even", 4, True, True), ("ragged_drop", 5, True, True),
+                                                ("ragged_keep", 5, False, True), ("noshuffle", 3, True, False)]:
+        dl = BatchedDataLoader(ArrayDict(leaves), BatchSpec(T, B), n_batches=n_batches, drop_last=drop_last,
+                               shuffle=shuffle)
+        dl.seed(9)
+        n = 0
+        for epoch in range(2):
+            for batch in dl.batches():
+                for k in batch:
+                    ref = g[f"{name}_{n}_{k}"]
+                    got = batch[k].cpu().numpy()
+                    assert got.shape == ref.shape and got.dtype == ref.dtype, (name, n, k)
+                    assert np.array_equal(got, ref), (name, n, k)
+                n += 1
+        assert n == int(g[f"{name}_meta"][3])
+        assert len(dl) == T * B
+
+
+def test_batched_dataloader_recurrent_and_batch_only_fields():
+    """Recurrent mode gathers whole [T] columns; batch_only_fields are indexed by env only
+    (batched_dataloader.py:75-87,104-106) -- checked against torch advanced indexing."""
+    from parllel_b200 import ArrayDict, BatchSpec
+    from parllel_b200.replays import BatchedDataLoader
+    T, B = 12, 10
+    rng = np.random.default_rng(3)
+    tree = ArrayDict({
+        "observation": torch.from_numpy(rng.standard_normal((T, B, 7)).astype(np.float32)).cuda(),
+        "valid": torch.from_numpy(rng.random((T, B)) < 0.8).cuda(),
+        "initial_rnn_state": torch.from_numpy(rng.standard_normal((B, 3)).astype(np.float32)).cuda(),
+    })
+    dl = BatchedDataLoader(tree, BatchSpec(T, B), n_batches=3, recurrent=True, batch_only_fields=["initial_rnn_state"])
+    dl.seed(1)
+    ref_rng = np.random.default_rng(1)
+    order = np.arange(B, dtype=np.int32)
+    ref_rng.shuffle(order)
+    batches = list(dl.batches())
+    assert len(batches) == 3
+    for i, batch in enumerate(batches):
+        idx = torch.from_numpy(order[i * 3:(i + 1) * 3].astype(np.int64)).cuda()
+        assert torch.equal(batch["observation"], tree["observation"][:, idx])
+        assert torch.equal(batch["valid"], tree["valid"][:, idx])
+        assert torch.equal(batch["initial_rnn_state"], tree["initial_rnn_state"][idx])

@@ -106,7 +106,7 @@ def main():
         B, shape = 1024, (3, 84, 84)
         obs = torch.randn((4, B) + shape, device=dev) * 3 + 5
         tf = NormalizeObservations({"observation": obs}, obs_shape=shape, initial_count=10000)
-        us = timed(lambda i: tf._step(obs[i % 4], None, dev), args.reps, flush)
+        us = timed(lambda i: tf._step(obs[i % 4], None, dev), args.reps, flush, args.inner)
         nbytes = 8 * B * int(np.prod(shape))
     elif args.what == "gather":
         size_T, Bn = 62464, 16
@@ -120,7 +120,7 @@ def main():
         rb._full, rb._cursor = True, 384
         rb.seed(0)
         idx = [tuple(torch.from_numpy(a).to(dev) for a in rb.sample_indices()) for _ in range(4)]
-        us = timed(lambda i: rb.gather(*idx[i % 4]), args.reps, flush)
+        us = timed(lambda i: rb.gather(*idx[i % 4]), args.reps, flush, args.inner)
         nbytes = 1114 * args.n
     else:
         raise SystemExit(f"unknown kernel {args.what}")
