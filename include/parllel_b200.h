@@ -150,6 +150,16 @@ PLB_API int plb_merge_moments_f64(
     const double *parts, int32_t n_parts, int64_t n_cols, int layout, double *out,
     plb_stream_t stream);
 
+/* The same exchange as ONE kernel over NVLink peer memory (no NCCL on the path): all-gather of the
+ * per-rank moments by direct P2P stores into every rank's symmetric buffer + release/acquire flags
+ * at system scope + the rank-ordered merge.  `peer_buffers` is a DEVICE array of `world` pointers to
+ * every rank's exchange buffer as mapped into this process (e.g. torch symmetric memory), each
+ * plb_exchange_buffer_bytes() long and zero-filled once.  One process per GPU. */
+PLB_API size_t plb_exchange_buffer_bytes(int32_t world, int64_t n_vals);
+PLB_API int plb_exchange_moments_p2p(
+    const double *local, int64_t n_vals, void *const *peer_buffers, int32_t rank, int32_t world,
+    int layout, int64_t n_cols, double *merged_out, plb_stream_t stream);
+
 /* parllel/transforms/running_mean_std.py:7-32 (update_from_moments): float64 Chan merge
  * of device-resident batch moments into the device-resident running state
  * (mean[n], var[n], count[1]).  batch_var = batch_m2 / batch_count. */

@@ -76,6 +76,8 @@ _SIGNATURES = {
         [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
          c_void_p], c_int),
     "plb_merge_moments_f64": ([c_void_p, c_int32, c_int64, c_int, c_void_p, c_void_p], c_int),
+    "plb_exchange_buffer_bytes": ([c_int32, c_int64], c_size_t),
+    "plb_exchange_moments_p2p": ([c_void_p, c_int64, c_void_p, c_int32, c_int32, c_int, c_int64, c_void_p, c_void_p], c_int),
     "plb_update_from_moments_f64": (
         [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p], c_int),
     "plb_scale_clip_f32": (

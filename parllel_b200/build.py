@@ -15,7 +15,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libparllel_b200.so")
 SOURCES = ["plb_api.cu", "plb_scan.cu", "plb_stats.cu", "plb_norm.cu", "plb_gather.cu",
-           "plb_obs.cu", "plb_pipeline.cu", "plb_rng.cu"]
+           "plb_obs.cu", "plb_pipeline.cu", "plb_exchange.cu", "plb_rng.cu"]
 HEADERS = ["plb_common.cuh", "plb_scan_shared.cuh", os.path.join("..", "..", "include", "parllel_b200.h")]
 
 NVCC_FLAGS = [

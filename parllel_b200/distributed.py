@@ -41,6 +41,67 @@ def merge_gathered_moments(gathered: torch.Tensor, n_cols: int, layout: int, out
     _lib.check(rc, "plb_merge_moments_f64")
 
 
+class PeerExchange:
+    """All-gather + rank-ordered merge of per-rank moments in ONE kernel over NVLink peer memory
+    (csrc/plb_exchange.cu): direct P2P stores into every rank's symmetric buffer, release/acquire
+    flags at system scope, no NCCL on the path.  The symmetric buffers come from
+    ``torch.distributed._symmetric_memory`` (plumbing); the kernel is graph-capturable because its
+    epoch counter lives in device memory.  One process per GPU."""
+
+    def __init__(self, n_vals: int, group=None, device=None) -> None:
+        import torch.distributed._symmetric_memory as symm_mem
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self.n_vals = int(n_vals)
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        nbytes = _lib.load().plb_exchange_buffer_bytes(self.world, self.n_vals)
+        self.buffer = symm_mem.empty(nbytes, dtype=torch.uint8, device=self.device)
+        self.buffer.zero_()
+        self.handle = symm_mem.rendezvous(self.buffer, self.group)
+        self.peer_table = torch.tensor([int(p) for p in self.handle.buffer_ptrs], dtype=torch.int64, device=self.device)
+        torch.cuda.synchronize(self.device)
+        dist.barrier(self.group)  # every rank's buffer is zeroed and mapped before the first exchange
+
+    def exchange(self, local: torch.Tensor, merged_out: torch.Tensor, layout: int, n_cols: int) -> None:
+        assert local.numel() == self.n_vals and local.dtype == torch.float64 and local.is_contiguous()
+        rc = _lib.load().plb_exchange_moments_p2p(local.data_ptr(), self.n_vals, self.peer_table.data_ptr(),
+                                                  self.rank, self.world, layout, n_cols, merged_out.data_ptr(),
+                                                  stream_ptr(self.device))
+        _lib.check(rc, "plb_exchange_moments_p2p")
+
+
+_peer_exchanges: dict = {}
+_peer_exchange_failed = False
+
+
+def exchange_moments(moments: torch.Tensor, n_cols: int, layout: int, group=None) -> None:
+    """In-place exchange of a rank's moments: afterwards ``moments`` holds the rank-ordered merge over
+    the whole group.  Uses the peer-memory kernel when symmetric memory is available (default; set
+    ``PLB_EXCHANGE=nccl`` to force the NCCL all-gather + merge-kernel path), else NCCL."""
+    import os
+    global _peer_exchange_failed
+    use_p2p = os.environ.get("PLB_EXCHANGE", "p2p") == "p2p" and moments.is_cuda and not _peer_exchange_failed \
+        and moments.numel() <= 4096
+    if use_p2p:
+        key = (id(group), moments.numel(), moments.device.index)
+        ex = _peer_exchanges.get(key)
+        if ex is None:
+            try:
+                ex = PeerExchange(moments.numel(), group, moments.device)
+                _peer_exchanges[key] = ex
+            except Exception as err:  # symmetric memory unavailable on this system: fall back to NCCL
+                import warnings
+                warnings.warn(f"peer-memory exchange unavailable ({err!r}); using NCCL all-gather")
+                _peer_exchange_failed = True
+                ex = None
+        if ex is not None:
+            ex.exchange(moments, moments, layout, n_cols)
+            return
+    gathered = all_gather_moments(moments, group)
+    merge_gathered_moments(gathered, n_cols, layout, moments)
+
+
 class ShardedNormalizeAdvantage(NormalizeAdvantage):
     """``NormalizeAdvantage`` over a B-sharded batch: local moments -> all-gather -> merge ->
     local normalise.  Every rank normalises with the statistics of the WHOLE batch."""
@@ -52,9 +113,7 @@ class ShardedNormalizeAdvantage(NormalizeAdvantage):
     def _exchange(self, moments: torch.Tensor, inner: int) -> None:
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self.group) == 1:
             return
-        local = moments[: 3 * inner]
-        gathered = all_gather_moments(local, self.group)
-        merge_gathered_moments(gathered, inner, 0, local)
+        exchange_moments(moments[: 3 * inner], inner, 0, self.group)
 
 
 def shard_statistics(transform, group=None):

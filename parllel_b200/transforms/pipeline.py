@@ -70,9 +70,8 @@ class FusedBatchTransforms(Transform):
         return dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
 
     def _exchange(self, moments: torch.Tensor) -> None:
-        from ..distributed import all_gather_moments, merge_gathered_moments
-        gathered = all_gather_moments(moments, self.group)
-        merge_gathered_moments(gathered, 1, 0, moments)
+        from ..distributed import exchange_moments
+        exchange_moments(moments, 1, 0, self.group)
 
     @staticmethod
     def _address(leaf) -> int:

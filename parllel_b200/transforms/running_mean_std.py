@@ -100,6 +100,5 @@ class RunningMeanStd:
                                                        self._n, flags, s), "plb_update_from_moments_f64")
 
     def _exchange(self, layout: int) -> None:
-        from ..distributed import all_gather_moments, merge_gathered_moments
-        gathered = all_gather_moments(self._moments, self.group)
-        merge_gathered_moments(gathered, 1 if layout == 0 else self._n, layout, self._moments)
+        from ..distributed import exchange_moments
+        exchange_moments(self._moments, 1 if layout == 0 else self._n, layout, self.group)
