@@ -42,6 +42,10 @@ static int run_pipeline(const plb_batch_pipeline *d, int phases, cudaStream_t st
     unsigned char *ws = reinterpret_cast<unsigned char *>(d->workspace);
     void *ws_a = ws, *ws_b = ws + MOMENTS_WS_BYTES;
     int rc;
+    // whole chain in one call on one GPU: the advantage scan only publishes per-CTA partial sums and
+    // the normalise kernel reduces them in its prologue (no serial last-CTA epilogue in the scan)
+    const bool direct_partials = (phases == PLB_PHASE_ALL) && est_adv && norm_adv && (T * B) % 4 == 0;
+    bool adv_partials_published = false;
 
     // ---------------------------------------------------------------- phase A
     if ((phases & PLB_PHASE_A) && norm_rew) {
@@ -87,12 +91,14 @@ static int run_pipeline(const plb_batch_pipeline *d, int phases, cudaStream_t st
             if (norm_adv) {
                 f.valid = d->valid; f.ld_valid = d->ld_valid;
                 f.tail = make_tail(d->advantage_moments, ws_b);
+                f.tail.partials_only = direct_partials ? 1 : 0;
             }
             const int mode = (d->gae_lambda == 1.0) ? 1 : 0;
             rc = scan_reverse(mode, d->reward, d->ld_reward, d->value, d->ld_value, d->done, d->ld_done,
                               d->bootstrap_value, d->advantage, d->ld_advantage, d->return_, d->ld_return,
                               T, B, 1, d->discount, d->gae_lambda, PLB_ALGO_CHUNKED,
                               (has_pre || norm_adv) ? &f : nullptr, stream);
+            if (rc == PLB_OK && norm_adv && direct_partials) adv_partials_published = true;
             if (rc == PLB_ERR_UNSUPPORTED) {  // unfused fallback, same results
                 if (has_pre) {
                     rc = plb_scale_clip_f32(d->reward, d->ld_reward, T, B, f.reward_var, d->eps_reward, lo, hi, stream);
@@ -123,6 +129,15 @@ static int run_pipeline(const plb_batch_pipeline *d, int phases, cudaStream_t st
     }
 
     // ---------------------------------------------------------------- phase C
+    if ((phases & PLB_PHASE_C) && norm_adv && adv_partials_published) {
+        rc = normalize_advantage_from_partials(d->advantage, d->ld_advantage, T, B, ws_b, d->eps_advantage,
+                                               d->advantage_moments, stream);
+        if (rc == PLB_OK) return PLB_OK;
+        if (rc != PLB_ERR_UNSUPPORTED) return rc;
+        // not 128-bit addressable: finish the reduction with a one-CTA pass, then the generic kernel
+        rc = finalize_published_partials(ws_b, d->advantage_moments, stream);
+        if (rc) return rc;
+    }
     if ((phases & PLB_PHASE_C) && norm_adv) {
         rc = plb_normalize_advantage_f32(d->advantage, d->ld_advantage, T, B, 1, d->advantage_moments,
                                          d->eps_advantage, stream);

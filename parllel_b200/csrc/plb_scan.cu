@@ -493,15 +493,14 @@ scan_chunked_kernel(const __grid_constant__ TensorMaps tm, const Params p)
     }
 
     __syncthreads();
-    if (threadIdx.x == 0) {
-        if (st_pending) store_tile(par ^ 1);
-        tma_store_wait<0>();  // smem must stay alive (and global writes complete) before the CTA retires
-    }
-    if (HAS_STATS) {
+    if (threadIdx.x == 0 && st_pending) store_tile(par ^ 1);  // last tile's outputs -> global (async)
+    if (HAS_STATS) {  // the grid reduction overlaps the drain of the last stores
         Sums acc;
         acc.n = (double)st_n; acc.s1 = st_s1; acc.s2 = st_s2; acc.piv = (double)st_piv;
         moments_tail(acc, p.tail, red_scratch);
     }
+    // smem must stay alive (and the global writes complete) before the CTA retires
+    if (threadIdx.x == 0) tma_store_wait<0>();
 }
 
 }  // namespace chunked

@@ -19,7 +19,9 @@ constexpr size_t MOMENTS_WS_BYTES = 64 + sizeof(Sums) * MOMENTS_MAX_PARTIALS;
 struct MomentsTail {
     double *moments_out;  // [3] = (count, mean, M2); nullptr disables the tail
     Sums *partials;
-    unsigned *ticket;
+    unsigned *ticket;     // workspace word 0: last-CTA ticket; word 1: number of partials written
+    int partials_only;    // 1: every CTA only publishes its partial Sums (and the CTA count); the
+                          //    consumer kernel reduces them itself (no serial last-CTA epilogue)
 };
 
 static inline MomentsTail make_tail(double *moments_out, void *workspace)
@@ -28,6 +30,7 @@ static inline MomentsTail make_tail(double *moments_out, void *workspace)
     t.moments_out = moments_out;
     t.ticket = reinterpret_cast<unsigned *>(workspace);
     t.partials = reinterpret_cast<Sums *>(reinterpret_cast<unsigned char *>(workspace) + 64);
+    t.partials_only = 0;
     return t;
 }
 
@@ -61,6 +64,9 @@ int column_moments(const float *x, int64_t ld_x, int64_t rows, int64_t cols, con
 int obs_step_single_pass(float *x, int64_t ld, int64_t rows, int64_t cols, const uint8_t *row_valid,
                          double *mean, double *var, const double *count, double *batch_count_out,
                          double eps, int flags, cudaStream_t stream);
+int finalize_published_partials(void *tail_workspace, double *moments_out, cudaStream_t stream);
+int normalize_advantage_from_partials(float *x, int64_t ld_x, int64_t rows, int64_t cols, void *tail_workspace,
+                                      double eps, double *moments_out, cudaStream_t stream);
 int make_tensor_map_2d(CUtensorMap *tm, const void *base, int elem_bytes, int64_t rows, int64_t cols,
                        int64_t ld_elems, int box_rows, int box_cols);
 
@@ -175,6 +181,13 @@ __device__ __forceinline__ void moments_tail(const Sums &mine, const MomentsTail
     __shared__ bool is_last;
     __syncthreads();  // scratch may have been used before
     const Sums blk = block_reduce_sums(mine, scratch);
+    if (tail.partials_only) {
+        if (threadIdx.x == 0) {
+            tail.partials[blockIdx.x] = blk;
+            if (blockIdx.x == 0) tail.ticket[1] = gridDim.x;
+        }
+        return;
+    }
     if (threadIdx.x == 0) {
         tail.partials[blockIdx.x] = blk;
         __threadfence();
@@ -211,6 +224,27 @@ __device__ __forceinline__ void moments_tail(const Sums &mine, const MomentsTail
         tail.moments_out[2] = m.m2;
         *tail.ticket = 0u;  // ready for the next launch
     }
+}
+// Block-cooperative reduction of the partial Sums a producer grid published with `partials_only`:
+// every CTA of the consumer derives the same moments (same data, same order).  Result in thread 0.
+__device__ __forceinline__ Moments reduce_published_partials(const Sums *partials, unsigned n, Sums *scratch)
+{
+    Sums acc;
+    acc.n = 0.0; acc.s1 = 0.0; acc.s2 = 0.0; acc.piv = 0.0;
+    const unsigned per = (n + blockDim.x - 1) / blockDim.x;
+    const unsigned lo = threadIdx.x * per;
+    for (unsigned i = lo; i < lo + per && i < n; ++i) {
+        Sums q = partials[i];
+        if (q.n > 0.0) {
+            if (acc.n == 0.0) acc = q;
+            else {
+                q = rebase(q, acc.piv);
+                acc.n += q.n; acc.s1 += q.s1; acc.s2 += q.s2;
+            }
+        }
+    }
+    acc = block_reduce_sums(acc, scratch);
+    return to_moments(acc);
 }
 #endif  // __CUDACC__
 

@@ -197,6 +197,24 @@ merge_moments_kernel(const double *__restrict__ parts, int n_parts, int64_t n_co
     }
 }
 
+__global__ void __launch_bounds__(256)
+finalize_partials_kernel(const Sums *partials, const unsigned *n_partials, double *moments_out)
+{
+    __shared__ Sums scratch[32];
+    const Moments m = reduce_published_partials(partials, *n_partials, scratch);
+    if (threadIdx.x == 0) {
+        moments_out[0] = m.n; moments_out[1] = m.mean; moments_out[2] = m.m2;
+    }
+}
+
+int finalize_published_partials(void *tail_workspace, double *moments_out, cudaStream_t stream)
+{
+    const MomentsTail t = make_tail(moments_out, tail_workspace);
+    finalize_partials_kernel<<<1, 256, 0, stream>>>(t.partials, t.ticket + 1, moments_out);
+    PLB_LAUNCH_CHECK();
+    return PLB_OK;
+}
+
 int column_moments_splits(int64_t rows, int64_t cols)
 {
     // enough CTAs to fill the machine: column blocks x row splits ~ 8 waves of 148
