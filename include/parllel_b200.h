@@ -225,6 +225,18 @@ PLB_API int plb_gather_tree(
     const int64_t *t_idx, const int64_t *b_idx, int64_t n,
     plb_stream_t stream);
 
+/* ReplayBuffer.sample_batch index generation on the device   parllel/replays/replay.py:55-70
+ *   T_idxs = rng.integers(0, valid_length, n) (+ (cursor + oldest_invalid)) % size_T when full),
+ *   B_idxs = rng.integers(0, B, n), T draw before B draw, for `k` consecutive minibatches,
+ * bit-exact with numpy.random.Generator(PCG64) (Lemire rejection on 32-bit half-words, the
+ * half-word buffer persisting across calls).  `pcg64_state` is DEVICE memory, 5 x uint64:
+ * {state_hi, state_lo, inc_hi, inc_lo, has_uint32 | (uinteger << 32)} exactly as numpy's
+ * bit_generator.state reports them; it is advanced in place.  Outputs are int64 [k, n]. */
+PLB_API int plb_replay_sample_indices(
+    uint64_t *pcg64_state, int64_t size_T, int64_t B, int64_t cursor, int full,
+    int64_t newest_invalid, int64_t oldest_invalid, int64_t n, int64_t k,
+    int64_t *t_idx, int64_t *b_idx, plb_stream_t stream);
+
 /* ------------------------------------------------------------------------------------
  * Fused batch-transform chain        parllel/samplers/basic.py:124-125 (`for transform in
  * batch_transforms: sample_tree = transform(sample_tree)`) specialised to the chain the examples

@@ -92,14 +92,14 @@ _SIGNATURES = {
          c_void_p, c_size_t, c_void_p], c_int),
     "plb_gather_tree": (
         [ctypes.POINTER(GatherLeaf), c_int32, c_void_p, c_void_p, c_int64, c_void_p], c_int),
+    "plb_replay_sample_indices": (
+        [c_void_p, c_int64, c_int64, c_int64, c_int, c_int64, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p], c_int),
     "plb_batch_pipeline_workspace_bytes": ([], c_size_t),
     "plb_batch_pipeline_f32": ([ctypes.POINTER(BatchPipeline), c_int, c_void_p], c_int),
 }
 
 # entry points added after the first release are bound when present (see include/parllel_b200.h)
-_OPTIONAL = {
-    "plb_replay_sample_indices": None,
-}
+_OPTIONAL = {}
 
 _lib = None
 

@@ -58,9 +58,15 @@ class ReplayBuffer:
         oldest_n_samples_invalid: int = 0,
         batch_transform: Optional[Callable] = None,
         device=None,
+        device_rng: bool = False,
     ) -> None:
         """Stores more than a batch's worth of samples in a circular buffer for off-policy
-        algorithms to sample from."""
+        algorithms to sample from.
+
+        ``device_rng=True`` draws the indices on the GPU (csrc/plb_rng.cu, bit-exact with the host
+        ``numpy.random.Generator`` stream) so a minibatch needs no host->device copy at all."""
+        self.device_rng = device_rng
+        self._rng_state = None
         self.tree = tree
         self.batch_spec = sampler_batch_spec
         self.size_T = size_T
@@ -104,6 +110,31 @@ class ReplayBuffer:
 
     def seed(self, seed: Optional[int] = None) -> None:
         self._rng = random.default_rng(seed)
+        self._rng_state = None  # device copy of the PCG64 state is rebuilt lazily
+
+    def _device_rng_state(self) -> torch.Tensor:
+        """PCG64 state words in device memory, seeded from the numpy generator (SeedSequence hashing
+        stays numpy's; only the stream is continued on the device)."""
+        if self._rng_state is None:
+            st = self._rng.bit_generator.state
+            assert st["bit_generator"] == "PCG64"
+            s, inc, m = st["state"]["state"], st["state"]["inc"], (1 << 64) - 1
+            words = [s >> 64, s & m, inc >> 64, inc & m, (st["has_uint32"] & 1) | (int(st["uinteger"]) << 32)]
+            host = np.array(words, dtype=np.uint64).view(np.int64)
+            self._rng_state = torch.from_numpy(host.copy()).to(self.device)
+        return self._rng_state
+
+    def sample_indices_device(self, k: int = 1):
+        """``k`` minibatches of ``(T_idxs, B_idxs)`` drawn on the device: int64 CUDA tensors ``[k, n]``."""
+        n = self.batch_size
+        t = torch.empty((k, n), dtype=torch.int64, device=self.device)
+        b = torch.empty((k, n), dtype=torch.int64, device=self.device)
+        rc = _lib.load().plb_replay_sample_indices(
+            self._device_rng_state().data_ptr(), self.size_T, self.batch_spec.B, self._cursor, int(self._full),
+            self.newest_n_samples_invalid, self.oldest_n_samples_invalid, n, k, t.data_ptr(), b.data_ptr(),
+            stream_ptr(self.device))
+        _lib.check(rc, "plb_replay_sample_indices")
+        return t, b
 
     @property
     def replay_batch_size(self) -> int:
@@ -160,7 +191,11 @@ class ReplayBuffer:
         return _unflatten(zip(self._paths, outs))
 
     def sample_batch(self) -> ArrayDict:
-        T_idxs, B_idxs = self.sample_indices()
+        if self.device_rng:
+            t, b = self.sample_indices_device(1)
+            T_idxs, B_idxs = t[0], b[0]
+        else:
+            T_idxs, B_idxs = self.sample_indices()
         batch = self.gather(T_idxs, B_idxs)
         batch = self.batch_transform(batch)
         return batch
@@ -171,10 +206,14 @@ class ReplayBuffer:
         legal whenever the ring is not written in between -- SAC draws ``updates_per_optimize``
         minibatches per iteration that way (torch/algos/sac.py:112-115).  Leaves come back as
         ``[k, batch, *feat]``; ``batch_transform`` is applied to the stacked tree."""
-        idx = [self.sample_indices() for _ in range(k)]
-        T_all = np.concatenate([t for t, _ in idx])
-        B_all = np.concatenate([b for _, b in idx])
-        flat = self.gather(T_all, B_all)
+        if self.device_rng:
+            t, b = self.sample_indices_device(k)
+            flat = self.gather(t.reshape(-1), b.reshape(-1))
+        else:
+            idx = [self.sample_indices() for _ in range(k)]
+            T_all = np.concatenate([t for t, _ in idx])
+            B_all = np.concatenate([b for _, b in idx])
+            flat = self.gather(T_all, B_all)
         n = self.batch_size
         stacked = flat.apply(lambda leaf: leaf.reshape((k, n) + tuple(leaf.shape[1:])))
         return self.batch_transform(stacked)

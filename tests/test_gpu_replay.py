@@ -198,3 +198,64 @@ def test_batched_dataloader_recurrent_and_batch_only_fields():
         assert torch.equal(batch["observation"], tree["observation"][:, idx])
         assert torch.equal(batch["valid"], tree["valid"][:, idx])
         assert torch.equal(batch["initial_rnn_state"], tree["initial_rnn_state"][idx])
+
+
+@pytest.mark.parametrize("size_T,B,cursor,full,newest,oldest,n,k", [
+    (62464, 16, 384, True, 0, 1, 16384, 1),     # C3
+    (62464, 16, 384, True, 0, 1, 256, 7),       # K-fused minibatches
+    (64, 4, 24, True, 2, 3, 33, 5),             # odd sizes: the half-word buffer crosses calls
+    (64, 4, 40, False, 1, 0, 7, 3),             # ring not full yet
+    (2**31 + 11, 3, 5, True, 0, 0, 5000, 2),    # ~half of all words rejected
+    (1000003, 1, 17, True, 0, 0, 1025, 3),      # B == 1 draws nothing (numpy returns zeros)
+    (4, 2**32, 3, False, 0, 0, 300, 2),         # full 32-bit range: raw words
+])
+def test_device_index_generation_is_bit_exact_with_numpy(size_T, B, cursor, full, newest, oldest, n, k):
+    """plb_replay_sample_indices continues numpy's PCG64 stream bit for bit, state included."""
+    from parllel_b200 import _lib
+    gen = np.random.default_rng(123)
+    gen.integers(0, 10, size=3)  # leave a buffered half-word behind, like a generator in use
+    st = gen.bit_generator.state
+    s, inc, m = st["state"]["state"], st["state"]["inc"], (1 << 64) - 1
+    words = np.array([s >> 64, s & m, inc >> 64, inc & m, (st["has_uint32"] & 1) | (int(st["uinteger"]) << 32)],
+                     dtype=np.uint64)
+    state = torch.from_numpy(words.view(np.int64).copy()).cuda()
+    t = torch.empty((k, n), dtype=torch.int64, device="cuda")
+    b = torch.empty((k, n), dtype=torch.int64, device="cuda")
+    lib = _lib.load()
+    for rnd in range(2):  # the second round starts from the state the kernel left behind
+        _lib.check(lib.plb_replay_sample_indices(state.data_ptr(), size_T, B, cursor, int(full), newest, oldest, n, k,
+                                                 t.data_ptr(), b.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        for kk in range(k):
+            if full:
+                t_ref = (gen.integers(0, size_T - oldest - newest, size=(n,)) + cursor + oldest) % size_T
+            else:
+                t_ref = gen.integers(0, cursor - newest, size=(n,))
+            b_ref = gen.integers(0, B, size=(n,))
+            assert np.array_equal(t[kk].cpu().numpy(), t_ref), (rnd, kk)
+            assert np.array_equal(b[kk].cpu().numpy(), b_ref), (rnd, kk)
+    st = gen.bit_generator.state
+    got = state.cpu().numpy().view(np.uint64)
+    assert int(got[0]) == st["state"]["state"] >> 64 and int(got[1]) == st["state"]["state"] & m
+    assert int(got[4]) & 1 == st["has_uint32"]
+    if st["has_uint32"]:
+        assert int(got[4]) >> 32 == st["uinteger"]
+
+
+def test_replay_buffer_device_rng_matches_host_rng(golden):
+    from parllel_b200 import BatchSpec
+    from parllel_b200.replays import ReplayBuffer
+    g = golden("replay")
+    tree, T, B, size_T = _ring_tree(g, "cuda")
+    host = ReplayBuffer(tree, BatchSpec(T, B), size_T=size_T, replay_batch_size=33, oldest_n_samples_invalid=1)
+    dev = ReplayBuffer(tree, BatchSpec(T, B), size_T=size_T, replay_batch_size=33, oldest_n_samples_invalid=1,
+                       device_rng=True)
+    for rb in (host, dev):
+        rb._full, rb._cursor = True, 24
+        rb.seed(5)
+    for _ in range(4):
+        a, b = host.sample_batch(), dev.sample_batch()
+        for key in a:
+            assert torch.equal(a[key], b[key]), key
+    fa, fb = host.sample_batches(3), dev.sample_batches(3)
+    for key in fa:
+        assert torch.equal(fa[key], fb[key]), key
