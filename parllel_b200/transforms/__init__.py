@@ -1,6 +1,7 @@
 """B200-native drop-ins for parllel's batch transforms (parllel/transforms/__init__.py)."""
 from .advantage import EstimateAdvantage
 from .clip_rewards import ClipRewards
+from .multi_advantage import EstimateMultiAgentAdvantage
 from .norm_advantage import NormalizeAdvantage
 from .norm_obs import NormalizeObservations
 from .norm_rewards import NormalizeRewards
@@ -10,6 +11,7 @@ from .transform import Transform
 
 __all__ = [
     "EstimateAdvantage",
+    "EstimateMultiAgentAdvantage",
     "FusedBatchTransforms",
     "ClipRewards",
     "NormalizeAdvantage",

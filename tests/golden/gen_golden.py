@@ -176,6 +176,21 @@ def gen_multi_advantage():
         out[f"{i}_return_"] = ret
         out[f"{i}_norm_advantage"] = np.asarray(tree["advantage"]).copy()
     out["n_cases"] = np.array(len(cases))
+
+    # single critic: scalar value, advantage gets a trailing singleton axis (multi_advantage.py:78-85)
+    T, B = 24, 10
+    rng = np.random.default_rng(3100)
+    tree = make_batch_tree(T, B)
+    ins = fill_batch(tree, rng, T, B, 0.1)
+    tree["advantage"] = tree["agent_info"]["value"].new_array(feature_shape=(1,), storage="local")
+    tree = EstimateMultiAgentAdvantage(tree, discount=0.99, gae_lambda=0.95)(tree)
+    for k, v in ins.items():
+        out[f"single_{k}"] = v
+    out["single_advantage"] = np.asarray(tree["advantage"]).copy()
+    out["single_return_"] = np.asarray(tree["return_"]).copy()
+
+    # (the reference's markov-game branch calls np.stack on a generator, multi_advantage.py:118-121,
+    #  which numpy >= 1.24 rejects, so no golden vector can be produced for it with this image)
     save("multi_advantage", **out)
 
 
@@ -265,6 +280,10 @@ def gen_dataloader():
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1:  # regenerate selected fixtures only: python gen_golden.py multi_advantage
+        for name in sys.argv[1:]:
+            globals()[f"gen_{name}"]()
+        sys.exit(0)
     gen_advantage()
     gen_pipeline("pipeline_c0", T=128, B=16, p_done=0.01, n_batches=3, with_valid=False, seed=7)
     gen_pipeline("pipeline_valid", T=40, B=24, p_done=0.08, n_batches=3, with_valid=True, seed=8,

@@ -193,3 +193,49 @@ def test_bad_arguments_fail_loudly():
     assert rc == -1 and b"stride" in lib.plb_last_error()
     with pytest.raises(_lib.PlbError):
         _lib.check(rc, "gae")
+
+
+def test_estimate_multi_agent_advantage_problem_types(golden):
+    """EstimateMultiAgentAdvantage: independent critics and single critic against the reference's golden
+    outputs; markov game (per-agent rewards) against the oracle (the reference's own branch does not run
+    on numpy >= 1.24, see parllel_b200/transforms/multi_advantage.py)."""
+    from parllel_b200 import ArrayDict
+    from parllel_b200.transforms import EstimateMultiAgentAdvantage
+    g = golden("multi_advantage")
+    d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    for i in range(int(g["n_cases"])):  # independent critics
+        T, B, N, lam, gamma = g[f"{i}_meta"]
+        tree = ArrayDict({"reward": d(g[f"{i}_reward"]), "done": d(g[f"{i}_done"]),
+                          "agent_info": {"value": d(g[f"{i}_value"])}, "bootstrap_value": d(g[f"{i}_bootstrap_value"]),
+                          "advantage": torch.zeros_like(d(g[f"{i}_value"])), "return_": torch.zeros_like(d(g[f"{i}_value"]))})
+        EstimateMultiAgentAdvantage(tree, gamma, lam)(tree)
+        assert_within_tolerance(tree["advantage"].cpu().numpy(), g[f"{i}_advantage"], what=f"independent {i}")
+        assert_within_tolerance(tree["return_"].cpu().numpy(), g[f"{i}_return_"], what=f"independent {i}")
+    # single critic: advantage has a trailing singleton axis
+    v = d(g["single_value"])
+    tree = ArrayDict({"reward": d(g["single_reward"]), "done": d(g["single_done"]), "agent_info": {"value": v},
+                      "bootstrap_value": d(g["single_bootstrap_value"]),
+                      "advantage": torch.zeros(v.shape + (1,), device="cuda"), "return_": torch.zeros_like(v)})
+    EstimateMultiAgentAdvantage(tree, 0.99, 0.95)(tree)
+    assert_within_tolerance(tree["advantage"].cpu().numpy(), g["single_advantage"], what="single critic")
+    assert_within_tolerance(tree["return_"].cpu().numpy(), g["single_return_"], what="single critic")
+    with pytest.raises(ValueError):
+        EstimateMultiAgentAdvantage({"reward": v, "agent_info": {"value": v}, "advantage": v}, 0.99, 0.95)
+    # markov game vs the oracle
+    T, B, N = 20, 6, 3
+    rng = np.random.default_rng(9)
+    names = ["zeta", "alpha", "mid"]
+    rewards = {n: rng.standard_normal((T, B)).astype(np.float32) for n in names}
+    value = rng.standard_normal((T, B, N)).astype(np.float32)
+    done = rng.random((T, B)) < 0.1
+    boot = rng.standard_normal((B, N)).astype(np.float32)
+    tree = ArrayDict({"reward": {n: d(rewards[n]) for n in reversed(names)}, "action": {n: d(rewards[n]) for n in names},
+                      "done": d(done), "agent_info": {"value": d(value)}, "bootstrap_value": d(boot),
+                      "advantage": torch.zeros(T, B, N, device="cuda"), "return_": torch.zeros(T, B, N, device="cuda")})
+    EstimateMultiAgentAdvantage(tree, 0.99, 0.9)(tree)
+    stacked = np.stack([rewards[n] for n in names], axis=-1)
+    adv, ret = np.empty_like(value), np.empty_like(value)
+    O.compute_gae_advantage(stacked.reshape(T, B * N), value.reshape(T, B * N), np.repeat(done, N, axis=1),
+                            boot.reshape(-1), 0.99, 0.9, adv.reshape(T, B * N), ret.reshape(T, B * N))
+    assert_within_tolerance(tree["advantage"].cpu().numpy(), adv, what="markov game")
+    assert_within_tolerance(tree["return_"].cpu().numpy(), ret, what="markov game")
