@@ -87,12 +87,13 @@ struct ScaleClipOp {
     double eps;
     float lo, hi;
     double denom;
-    __device__ __forceinline__ void prepare() { denom = (var != nullptr) ? sqrt(__dadd_rn(*var, eps)) : 1.0; }
+    __device__ __forceinline__ void prepare() { denom = (var != nullptr) ? 1.0 / sqrt(__dadd_rn(*var, eps)) : 1.0; }
     __device__ __forceinline__ float operator()(float x, int64_t) const
     {
         if (var != nullptr) {
-            // one float64 division per element, like the reference (norm_rewards.py:114)
-            x = __double2float_rn(__ddiv_rn((double)x, denom));
+            // float64 product with the reciprocal of sqrt(var + eps): <= 1 ulp(float64) from the reference's
+            // float64 division (norm_rewards.py:114) before the single rounding to float32
+            x = __double2float_rn(__dmul_rn((double)x, denom));
         }
         return fminf(fmaxf(x, lo), hi);
     }

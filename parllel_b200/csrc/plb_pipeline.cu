@@ -46,6 +46,10 @@ static int run_pipeline(const plb_batch_pipeline *d, int phases, cudaStream_t st
     // the normalise kernel reduces them in its prologue (no serial last-CTA epilogue in the scan)
     const bool direct_partials = (phases == PLB_PHASE_ALL) && est_adv && norm_adv && (T * B) % 4 == 0;
     bool adv_partials_published = false;
+    // same idea for the reward statistics: on one GPU the CTA that finishes the past-return moments
+    // also applies update_from_moments to the running state (no separate update launch)
+    const bool update_in_tail = (phases == PLB_PHASE_ALL) && norm_rew;
+    bool state_updated = false;
 
     // ---------------------------------------------------------------- phase A
     if ((phases & PLB_PHASE_A) && norm_rew) {
@@ -54,8 +58,15 @@ static int run_pipeline(const plb_batch_pipeline *d, int phases, cudaStream_t st
         ScanFusion f = {};
         f.valid = d->valid; f.ld_valid = d->ld_valid;
         f.tail = make_tail(d->return_moments, ws_a);
+        if (update_in_tail) {
+            PLB_REQUIRE(d->return_mean && d->return_var && d->return_count, PLB_ERR_INVALID_ARGUMENT,
+                        "NormalizeRewards stage: missing running statistics");
+            f.tail.upd_mean = d->return_mean; f.tail.upd_var = d->return_var; f.tail.upd_count = d->return_count;
+            f.tail.upd_flags = d->moments_flags;
+        }
         rc = scan_forward(d->reward, d->ld_reward, d->done, d->ld_done, d->previous_return, d->previous_done,
                           d->past_return, d->ld_past_return, T, B, d->discount, PLB_ALGO_CHUNKED, &f, stream);
+        if (rc == PLB_OK && update_in_tail) state_updated = true;
         if (rc == PLB_ERR_UNSUPPORTED) {  // shape TMA cannot describe: serial scan + separate moments
             rc = scan_forward(d->reward, d->ld_reward, d->done, d->ld_done, d->previous_return, d->previous_done,
                               d->past_return, d->ld_past_return, T, B, d->discount, PLB_ALGO_SERIAL, nullptr, stream);
@@ -68,7 +79,7 @@ static int run_pipeline(const plb_batch_pipeline *d, int phases, cudaStream_t st
 
     // ---------------------------------------------------------------- phase B
     if (phases & PLB_PHASE_B) {
-        if (norm_rew) {
+        if (norm_rew && !state_updated) {
             PLB_REQUIRE(d->return_mean && d->return_var && d->return_count, PLB_ERR_INVALID_ARGUMENT,
                         "NormalizeRewards stage: missing running statistics");
             rc = plb_update_from_moments_f64(d->return_moments, d->return_moments + 1, d->return_moments + 2,

@@ -22,6 +22,10 @@ struct MomentsTail {
     unsigned *ticket;     // workspace word 0: last-CTA ticket; word 1: number of partials written
     int partials_only;    // 1: every CTA only publishes its partial Sums (and the CTA count); the
                           //    consumer kernel reduces them itself (no serial last-CTA epilogue)
+    // optional: the CTA that finishes the reduction also folds the batch moments into a scalar
+    // running state (update_from_moments, running_mean_std.py:7-32) -- saves a kernel launch
+    double *upd_mean, *upd_var, *upd_count;
+    int upd_flags;
 };
 
 static inline MomentsTail make_tail(double *moments_out, void *workspace)
@@ -31,6 +35,8 @@ static inline MomentsTail make_tail(double *moments_out, void *workspace)
     t.ticket = reinterpret_cast<unsigned *>(workspace);
     t.partials = reinterpret_cast<Sums *>(reinterpret_cast<unsigned char *>(workspace) + 64);
     t.partials_only = 0;
+    t.upd_mean = t.upd_var = t.upd_count = nullptr;
+    t.upd_flags = 0;
     return t;
 }
 
@@ -170,6 +176,32 @@ __device__ __forceinline__ void bulk_store_1d(void *dst, const void *src, uint32
                  : "memory");
 }
 
+// running_mean_std.py:23-30 for one feature: (mean, var) <- Chan merge with batch moments
+// (b_n, b_mean, b_m2); `cnt` is the running count BEFORE the update.  Same operation order as
+// the reference; PLB_MOMENTS_F32_FLOW reproduces numba's float32 `batch_var * batch_count`.
+__device__ __forceinline__ void chan_update_scalar(double b_n, double b_mean, double b_m2, double cnt, int flags,
+                                                   double &mean, double &var)
+{
+    double batch_mean = b_mean;
+    double batch_var = b_m2 / b_n;
+    double m_b;
+    if (flags & PLB_MOMENTS_F32_FLOW) {
+        batch_mean = (double)__double2float_rn(batch_mean);
+        const float bv32 = __double2float_rn(batch_var);
+        m_b = (double)__fmul_rn(bv32, __double2float_rn(b_n));  // float32 array * int64 scalar -> float32
+    } else {
+        m_b = __dmul_rn(batch_var, b_n);
+    }
+    const double delta = __dsub_rn(batch_mean, mean);
+    const double total = __dadd_rn(b_n, cnt);
+    const double new_mean = __dadd_rn(mean, __ddiv_rn(__dmul_rn(delta, b_n), total));
+    const double m_a = __dmul_rn(var, cnt);
+    const double cross = __ddiv_rn(__dmul_rn(__dmul_rn(__dmul_rn(delta, delta), cnt), b_n), total);
+    const double m_2 = __dadd_rn(__dadd_rn(m_a, m_b), cross);
+    mean = new_mean;
+    var = __ddiv_rn(m_2, total);
+}
+
 // ---------------------------------------------------------------------------------
 // Grid-wide moments tail: every CTA contributes one partial (division-free Sums); the last CTA
 // to arrive rebases all partials to one pivot, adds them in a fixed order (deterministic) and
@@ -222,6 +254,14 @@ __device__ __forceinline__ void moments_tail(const Sums &mine, const MomentsTail
         tail.moments_out[0] = m.n;
         tail.moments_out[1] = m.mean;
         tail.moments_out[2] = m.m2;
+        if (tail.upd_mean != nullptr) {
+            double mean = *tail.upd_mean, var = *tail.upd_var;
+            const double cnt = *tail.upd_count;
+            chan_update_scalar(m.n, m.mean, m.m2, cnt, tail.upd_flags, mean, var);
+            *tail.upd_mean = mean;
+            *tail.upd_var = var;
+            *tail.upd_count = m.n + cnt;
+        }
         *tail.ticket = 0u;  // ready for the next launch
     }
 }

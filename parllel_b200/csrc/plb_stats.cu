@@ -123,31 +123,6 @@ column_moments_finalize_kernel(const Moments *__restrict__ partials, int64_t col
 // update_from_moments: single CTA so that the shared `count` is read by everyone
 // before it is overwritten.
 // ---------------------------------------------------------------------------------
-__device__ __forceinline__ void chan_update(double b_n, double b_mean, double b_m2, double cnt, int flags,
-                                            double &mean, double &var)
-{
-    // running_mean_std.py:23-30
-    double batch_mean = b_mean;
-    double batch_var = b_m2 / b_n;
-    double m_b;
-    if (flags & PLB_MOMENTS_F32_FLOW) {
-        batch_mean = (double)__double2float_rn(batch_mean);
-        const float bv32 = __double2float_rn(batch_var);
-        batch_var = (double)bv32;
-        m_b = (double)__fmul_rn(bv32, __double2float_rn(b_n));  // float32 array * int64 scalar -> float32
-    } else {
-        m_b = __dmul_rn(batch_var, b_n);
-    }
-    const double delta = __dsub_rn(batch_mean, mean);
-    const double total = __dadd_rn(b_n, cnt);
-    const double new_mean = __dadd_rn(mean, __ddiv_rn(__dmul_rn(delta, b_n), total));
-    const double m_a = __dmul_rn(var, cnt);
-    const double cross = __ddiv_rn(__dmul_rn(__dmul_rn(__dmul_rn(delta, delta), cnt), b_n), total);
-    const double m_2 = __dadd_rn(__dadd_rn(m_a, m_b), cross);
-    mean = new_mean;
-    var = __ddiv_rn(m_2, total);
-}
-
 __global__ void __launch_bounds__(1024)
 update_from_moments_kernel(const double *__restrict__ batch_count, const double *__restrict__ batch_mean,
                            const double *__restrict__ batch_m2, double *mean, double *var, double *count,
@@ -158,7 +133,7 @@ update_from_moments_kernel(const double *__restrict__ batch_count, const double 
     __syncthreads();
     for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
         double m = mean[i], v = var[i];
-        chan_update(b_n, batch_mean[i], batch_m2[i], cnt, flags, m, v);
+        chan_update_scalar(b_n, batch_mean[i], batch_m2[i], cnt, flags, m, v);
         mean[i] = m;
         var[i] = v;
     }
