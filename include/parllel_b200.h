@@ -277,6 +277,12 @@ typedef struct {
     double *advantage_moments;                       /* [3] batch moments of advantage     */
     int32_t moments_flags;                           /* PLB_MOMENTS_F32_FLOW or 0 */
     void *workspace; size_t workspace_bytes;
+    /* multi-GPU (B sharded), optional: with `xch_peers` != NULL and phases == PLB_PHASE_ALL both
+     * statistics are exchanged INSIDE the kernels over NVLink peer memory -- the scan that produces a
+     * statistic pushes the rank's moments into every peer's buffer from its last CTA, the kernel that
+     * consumes it waits for all ranks and merges in rank order in its prologue.  `xch_peers` is the
+     * DEVICE pointer table of plb_exchange_moments_p2p (buffers sized for n_vals = 3). */
+    void *const *xch_peers; int32_t xch_rank, xch_world;
 } plb_batch_pipeline;
 
 PLB_API size_t plb_batch_pipeline_workspace_bytes(void);

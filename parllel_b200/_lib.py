@@ -49,6 +49,7 @@ class BatchPipeline(ctypes.Structure):
         ("return_moments", c_void_p), ("advantage_moments", c_void_p),
         ("moments_flags", c_int32),
         ("workspace", c_void_p), ("workspace_bytes", c_size_t),
+        ("xch_peers", c_void_p), ("xch_rank", c_int32), ("xch_world", c_int32),
     ]
 
 

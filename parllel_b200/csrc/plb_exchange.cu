@@ -16,22 +16,12 @@
 // One process per GPU; never run two ranks of one exchange on the same GPU (they would spin on each
 // other without any guarantee of co-scheduling).
 #include "plb_common.cuh"
+#include "plb_scan_shared.cuh"
 
 namespace plb {
 
 constexpr int EX_MAX_WORLD = 64;
 constexpr size_t EX_HEADER_BYTES = 1024;  // epoch + flags, keeps data 1 KB aligned
-
-__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v)
-{
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p)
-{
-    uint32_t v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
 
 struct ExchangeParams {
     const double *local;      // [n_vals] this rank's moments
@@ -101,6 +91,31 @@ exchange_moments_kernel(const ExchangeParams p)
             p.merged_out[1 + p.n_cols + c] = acc.m2;
         }
     }
+}
+
+// wait + merge (+ optional running-state update) for moments pushed by a producer kernel's tail
+__global__ void __launch_bounds__(32)
+exchange_finish_kernel(const XchRef xch, double *moments_out, double *upd_mean, double *upd_var, double *upd_count,
+                       int upd_flags)
+{
+    const Moments m = xch_wait_merge3(xch);
+    if (threadIdx.x == 0) {
+        moments_out[0] = m.n; moments_out[1] = m.mean; moments_out[2] = m.m2;
+        if (upd_mean != nullptr) {
+            double mean = *upd_mean, var = *upd_var;
+            const double cnt = *upd_count;
+            chan_update_scalar(m.n, m.mean, m.m2, cnt, upd_flags, mean, var);
+            *upd_mean = mean; *upd_var = var; *upd_count = m.n + cnt;
+        }
+    }
+}
+
+int exchange_finish(const XchRef &xch, double *moments_out, double *upd_mean, double *upd_var, double *upd_count,
+                    int upd_flags, cudaStream_t stream)
+{
+    exchange_finish_kernel<<<1, 32, 0, stream>>>(xch, moments_out, upd_mean, upd_var, upd_count, upd_flags);
+    PLB_LAUNCH_CHECK();
+    return PLB_OK;
 }
 
 }  // namespace plb

@@ -195,6 +195,88 @@ normalize_advantage_partials_kernel(float *__restrict__ x, int64_t ld_x, int64_t
     }
 }
 
+// Multi-GPU variant: the producer's tail pushed this rank's moments to every peer; each CTA waits
+// for all ranks' flags and merges in rank order in its prologue (warp 0), the first loads in flight.
+__global__ void __launch_bounds__(256)
+normalize_advantage_xch_kernel(float *__restrict__ x, int64_t ld_x, int64_t rows, int64_t cols, const XchRef xch,
+                               float eps, double *__restrict__ moments_out)
+{
+    __shared__ float s_mean, s_denom;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+    const int64_t vpr = cols >> 2;
+    const int64_t total = rows * vpr;
+    constexpr int U = 4;
+    float4 v[U];
+    int64_t off[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const int64_t i = tid + (int64_t)u * nthreads;
+        if (i < total) {
+            const int64_t r = (rows == 1) ? 0 : i / vpr;
+            off[u] = r * ld_x + ((i - r * vpr) << 2);
+            v[u] = *reinterpret_cast<const float4 *>(x + off[u]);
+        }
+    }
+    if (threadIdx.x < 32) {
+        const Moments m = xch_wait_merge3(xch);
+        if (threadIdx.x == 0) {
+            s_mean = __double2float_rn(m.mean);
+            s_denom = __fadd_rn(__double2float_rn(sqrt(m.m2 / m.n)), eps);
+            if (blockIdx.x == 0) {
+                moments_out[0] = m.n; moments_out[1] = m.mean; moments_out[2] = m.m2;
+            }
+        }
+    }
+    __syncthreads();
+    const float mean = s_mean, denom = s_denom;
+    for (int64_t base = tid; base < total; base += nthreads * U) {
+        if (base != tid) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int64_t i = base + (int64_t)u * nthreads;
+                if (i < total) {
+                    const int64_t r = (rows == 1) ? 0 : i / vpr;
+                    off[u] = r * ld_x + ((i - r * vpr) << 2);
+                    v[u] = *reinterpret_cast<const float4 *>(x + off[u]);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t i = base + (int64_t)u * nthreads;
+            if (i < total) {
+                float4 o;
+                o.x = __fdiv_rn(__fsub_rn(v[u].x, mean), denom);
+                o.y = __fdiv_rn(__fsub_rn(v[u].y, mean), denom);
+                o.z = __fdiv_rn(__fsub_rn(v[u].z, mean), denom);
+                o.w = __fdiv_rn(__fsub_rn(v[u].w, mean), denom);
+                *reinterpret_cast<float4 *>(x + off[u]) = o;
+            }
+        }
+    }
+}
+
+int normalize_advantage_after_exchange(float *x, int64_t ld_x, int64_t rows, int64_t cols, const XchRef &xch, double eps,
+                                       double *moments_out, cudaStream_t stream)
+{
+    if (rows * cols == 0) return PLB_OK;
+    if (ld_x == cols) {
+        cols = rows * cols;
+        rows = 1;
+        ld_x = cols;
+    }
+    if (!((cols % 4 == 0) && (ld_x % 4 == 0) && aligned(x, 16))) return PLB_ERR_UNSUPPORTED;
+    const int sms = sm_count();
+    PLB_REQUIRE(sms > 0, PLB_ERR_UNSUPPORTED, "no CUDA device");
+    int64_t blocks = ceil_div(rows * cols / 4, 256 * 4);
+    if (blocks < 1) blocks = 1;
+    if (blocks > (int64_t)sms * 8) blocks = (int64_t)sms * 8;
+    normalize_advantage_xch_kernel<<<(unsigned)blocks, 256, 0, stream>>>(x, ld_x, rows, cols, xch, (float)eps, moments_out);
+    PLB_LAUNCH_CHECK();
+    return PLB_OK;
+}
+
 // returns PLB_ERR_UNSUPPORTED when the region cannot take the 128-bit path
 int normalize_advantage_from_partials(float *x, int64_t ld_x, int64_t rows, int64_t cols, void *tail_workspace,
                                       double eps, double *moments_out, cudaStream_t stream)

@@ -44,11 +44,20 @@ static int run_pipeline(const plb_batch_pipeline *d, int phases, cudaStream_t st
     int rc;
     // whole chain in one call on one GPU: the advantage scan only publishes per-CTA partial sums and
     // the normalise kernel reduces them in its prologue (no serial last-CTA epilogue in the scan)
-    const bool direct_partials = (phases == PLB_PHASE_ALL) && est_adv && norm_adv && (T * B) % 4 == 0;
+    const bool direct_partials = (phases == PLB_PHASE_ALL) && est_adv && norm_adv && (T * B) % 4 == 0 &&
+                                 !(d->xch_peers != nullptr && d->xch_world > 1);
     bool adv_partials_published = false;
     // same idea for the reward statistics: on one GPU the CTA that finishes the past-return moments
     // also applies update_from_moments to the running state (no separate update launch)
-    const bool update_in_tail = (phases == PLB_PHASE_ALL) && norm_rew;
+    // multi-GPU: exchange both statistics inside the kernels over peer memory
+    XchRef xch;
+    xch.peers = reinterpret_cast<unsigned char *const *>(d->xch_peers);
+    xch.rank = d->xch_rank; xch.world = d->xch_world;
+    const bool use_xch = (phases == PLB_PHASE_ALL) && xch.peers != nullptr && xch.world > 1;
+    PLB_REQUIRE(!use_xch || (xch.world <= 32 && xch.rank >= 0 && xch.rank < xch.world), PLB_ERR_INVALID_ARGUMENT,
+                "in-kernel exchange supports up to 32 ranks");
+    bool adv_pushed = false;
+    const bool update_in_tail = (phases == PLB_PHASE_ALL) && norm_rew && !use_xch;
     bool state_updated = false;
 
     // ---------------------------------------------------------------- phase A
@@ -64,15 +73,28 @@ static int run_pipeline(const plb_batch_pipeline *d, int phases, cudaStream_t st
             f.tail.upd_mean = d->return_mean; f.tail.upd_var = d->return_var; f.tail.upd_count = d->return_count;
             f.tail.upd_flags = d->moments_flags;
         }
+        if (use_xch) f.tail.xch = xch;
         rc = scan_forward(d->reward, d->ld_reward, d->done, d->ld_done, d->previous_return, d->previous_done,
                           d->past_return, d->ld_past_return, T, B, d->discount, PLB_ALGO_CHUNKED, &f, stream);
         if (rc == PLB_OK && update_in_tail) state_updated = true;
+        if (rc == PLB_OK && use_xch) {
+            // wait for every rank's push, merge in rank order, fold into the running state
+            PLB_REQUIRE(d->return_mean && d->return_var && d->return_count, PLB_ERR_INVALID_ARGUMENT,
+                        "NormalizeRewards stage: missing running statistics");
+            rc = exchange_finish(xch, d->return_moments, d->return_mean, d->return_var, d->return_count,
+                                 d->moments_flags, stream);
+            if (rc) return rc;
+            state_updated = true;
+        }
         if (rc == PLB_ERR_UNSUPPORTED) {  // shape TMA cannot describe: serial scan + separate moments
             rc = scan_forward(d->reward, d->ld_reward, d->done, d->ld_done, d->previous_return, d->previous_done,
                               d->past_return, d->ld_past_return, T, B, d->discount, PLB_ALGO_SERIAL, nullptr, stream);
             if (rc) return rc;
             rc = plb_batch_moments_f32(d->past_return, d->ld_past_return, T, B, d->valid, d->ld_valid,
                                        d->return_moments, ws_a, MOMENTS_WS_BYTES, stream);
+            if (rc == PLB_OK && use_xch)
+                rc = plb_exchange_moments_p2p(d->return_moments, 3, d->xch_peers, xch.rank, xch.world, 0, 1,
+                                              d->return_moments, stream);
         }
         if (rc) return rc;
     }
@@ -103,6 +125,7 @@ static int run_pipeline(const plb_batch_pipeline *d, int phases, cudaStream_t st
                 f.valid = d->valid; f.ld_valid = d->ld_valid;
                 f.tail = make_tail(d->advantage_moments, ws_b);
                 f.tail.partials_only = direct_partials ? 1 : 0;
+                if (use_xch) f.tail.xch = xch;
             }
             const int mode = (d->gae_lambda == 1.0) ? 1 : 0;
             rc = scan_reverse(mode, d->reward, d->ld_reward, d->value, d->ld_value, d->done, d->ld_done,
@@ -110,6 +133,7 @@ static int run_pipeline(const plb_batch_pipeline *d, int phases, cudaStream_t st
                               T, B, 1, d->discount, d->gae_lambda, PLB_ALGO_CHUNKED,
                               (has_pre || norm_adv) ? &f : nullptr, stream);
             if (rc == PLB_OK && norm_adv && direct_partials) adv_partials_published = true;
+            if (rc == PLB_OK && norm_adv && use_xch) adv_pushed = true;
             if (rc == PLB_ERR_UNSUPPORTED) {  // unfused fallback, same results
                 if (has_pre) {
                     rc = plb_scale_clip_f32(d->reward, d->ld_reward, T, B, f.reward_var, d->eps_reward, lo, hi, stream);
@@ -119,9 +143,13 @@ static int run_pipeline(const plb_batch_pipeline *d, int phases, cudaStream_t st
                                   d->bootstrap_value, d->advantage, d->ld_advantage, d->return_, d->ld_return,
                                   T, B, 1, d->discount, d->gae_lambda, PLB_ALGO_SERIAL, nullptr, stream);
                 if (rc) return rc;
-                if (norm_adv)
+                if (norm_adv) {
                     rc = plb_batch_moments_f32(d->advantage, d->ld_advantage, T, B, d->valid, d->ld_valid,
                                                d->advantage_moments, ws_b, MOMENTS_WS_BYTES, stream);
+                    if (rc == PLB_OK && use_xch)
+                        rc = plb_exchange_moments_p2p(d->advantage_moments, 3, d->xch_peers, xch.rank, xch.world, 0, 1,
+                                                      d->advantage_moments, stream);
+                }
             }
             if (rc) return rc;
         } else {
@@ -134,12 +162,23 @@ static int run_pipeline(const plb_batch_pipeline *d, int phases, cudaStream_t st
                 PLB_REQUIRE(d->advantage && d->advantage_moments, PLB_ERR_INVALID_ARGUMENT, "advantage is null");
                 rc = plb_batch_moments_f32(d->advantage, d->ld_advantage, T, B, d->valid, d->ld_valid,
                                            d->advantage_moments, ws_b, MOMENTS_WS_BYTES, stream);
+                if (rc == PLB_OK && use_xch)
+                    rc = plb_exchange_moments_p2p(d->advantage_moments, 3, d->xch_peers, xch.rank, xch.world, 0, 1,
+                                                  d->advantage_moments, stream);
                 if (rc) return rc;
             }
         }
     }
 
     // ---------------------------------------------------------------- phase C
+    if ((phases & PLB_PHASE_C) && norm_adv && adv_pushed) {
+        rc = normalize_advantage_after_exchange(d->advantage, d->ld_advantage, T, B, xch, d->eps_advantage,
+                                                d->advantage_moments, stream);
+        if (rc == PLB_OK) return PLB_OK;
+        if (rc != PLB_ERR_UNSUPPORTED) return rc;
+        rc = exchange_finish(xch, d->advantage_moments, nullptr, nullptr, nullptr, 0, stream);
+        if (rc) return rc;
+    }
     if ((phases & PLB_PHASE_C) && norm_adv && adv_partials_published) {
         rc = normalize_advantage_from_partials(d->advantage, d->ld_advantage, T, B, ws_b, d->eps_advantage,
                                                d->advantage_moments, stream);

@@ -16,6 +16,14 @@ namespace plb {
 constexpr int MOMENTS_MAX_PARTIALS = 4096;
 constexpr size_t MOMENTS_WS_BYTES = 64 + sizeof(Sums) * MOMENTS_MAX_PARTIALS;
 
+// Reference to the peer-mapped exchange buffers of plb_exchange.cu (n_vals = 3 layout):
+// peers == nullptr switches the in-kernel exchange off.
+struct XchRef {
+    unsigned char *const *peers;  // device array [world] of every rank's buffer, peer-mapped
+    int rank, world;
+};
+constexpr size_t XCH_HEADER_BYTES = 1024;  // uint32 epoch @0, uint32 flags[2][world] @64, data @1024
+
 struct MomentsTail {
     double *moments_out;  // [3] = (count, mean, M2); nullptr disables the tail
     Sums *partials;
@@ -26,6 +34,9 @@ struct MomentsTail {
     // running state (update_from_moments, running_mean_std.py:7-32) -- saves a kernel launch
     double *upd_mean, *upd_var, *upd_count;
     int upd_flags;
+    // optional (multi-GPU): the finishing CTA pushes the final moments straight into every peer's
+    // exchange buffer (NVLink P2P stores + release flags); the consumer kernel waits and merges
+    XchRef xch;
 };
 
 static inline MomentsTail make_tail(double *moments_out, void *workspace)
@@ -37,6 +48,7 @@ static inline MomentsTail make_tail(double *moments_out, void *workspace)
     t.partials_only = 0;
     t.upd_mean = t.upd_var = t.upd_count = nullptr;
     t.upd_flags = 0;
+    t.xch.peers = nullptr; t.xch.rank = 0; t.xch.world = 1;
     return t;
 }
 
@@ -71,6 +83,10 @@ int obs_step_single_pass(float *x, int64_t ld, int64_t rows, int64_t cols, const
                          double *mean, double *var, const double *count, double *batch_count_out,
                          double eps, int flags, cudaStream_t stream);
 int finalize_published_partials(void *tail_workspace, double *moments_out, cudaStream_t stream);
+int exchange_finish(const XchRef &xch, double *moments_out, double *upd_mean, double *upd_var, double *upd_count,
+                    int upd_flags, cudaStream_t stream);
+int normalize_advantage_after_exchange(float *x, int64_t ld_x, int64_t rows, int64_t cols, const XchRef &xch, double eps,
+                                       double *moments_out, cudaStream_t stream);
 int normalize_advantage_from_partials(float *x, int64_t ld_x, int64_t rows, int64_t cols, void *tail_workspace,
                                       double eps, double *moments_out, cudaStream_t stream);
 int make_tensor_map_2d(CUtensorMap *tm, const void *base, int elem_bytes, int64_t rows, int64_t cols,
@@ -176,6 +192,73 @@ __device__ __forceinline__ void bulk_store_1d(void *dst, const void *src, uint32
                  : "memory");
 }
 
+// ---------------------------------------------------------------------------------
+// In-kernel statistics exchange over peer memory (see plb_exchange.cu for the protocol)
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v)
+{
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Push this rank's (count, mean, M2) into slot [parity][rank] of every rank's buffer and raise the
+// flags.  Called by ONE full warp (world <= 32); lane 0 supplies the moments.
+__device__ __forceinline__ void xch_push3(const XchRef &x, double n, double mean, double m2)
+{
+    const int lane = threadIdx.x & 31;
+    unsigned char *mine = x.peers[x.rank];
+    uint32_t epoch = 0;
+    if (lane == 0) {
+        uint32_t *ep = reinterpret_cast<uint32_t *>(mine);
+        epoch = *ep + 1u;
+        *ep = epoch;
+    }
+    epoch = __shfl_sync(0xffffffffu, epoch, 0);
+    n = __shfl_sync(0xffffffffu, n, 0);
+    mean = __shfl_sync(0xffffffffu, mean, 0);
+    m2 = __shfl_sync(0xffffffffu, m2, 0);
+    const int par = (int)(epoch & 1u);
+    if (lane < x.world) {
+        unsigned char *peer = x.peers[lane];
+        double *dst = reinterpret_cast<double *>(peer + XCH_HEADER_BYTES) + ((size_t)par * x.world + x.rank) * 3;
+        dst[0] = n; dst[1] = mean; dst[2] = m2;
+        __threadfence_system();
+        st_release_sys(reinterpret_cast<uint32_t *>(peer + 64) + par * x.world + x.rank, epoch);
+    }
+}
+
+// Wait for every rank's moments of the current epoch and merge them in rank order.  Called by ONE
+// full warp; every lane returns the same merged moments.
+__device__ __forceinline__ Moments xch_wait_merge3(const XchRef &x)
+{
+    const int lane = threadIdx.x & 31;
+    const unsigned char *mine = x.peers[x.rank];
+    const uint32_t epoch = *reinterpret_cast<const volatile uint32_t *>(mine);
+    const int par = (int)(epoch & 1u);
+    if (lane < x.world) {
+        const uint32_t *flag = reinterpret_cast<const uint32_t *>(mine + 64) + par * x.world + lane;
+        const long long t0 = clock64();
+        while (ld_acquire_sys(flag) != epoch) {
+            if (clock64() - t0 > 20000000000LL) __trap();  // a peer died: do not hang the GPU forever
+        }
+    }
+    __syncwarp();
+    const volatile double *parts = reinterpret_cast<const volatile double *>(mine + XCH_HEADER_BYTES) + (size_t)par * x.world * 3;
+    Moments acc;
+    acc.n = 0.0; acc.mean = 0.0; acc.m2 = 0.0;
+    for (int r = 0; r < x.world; ++r) {
+        Moments m;
+        m.n = parts[3 * r]; m.mean = parts[3 * r + 1]; m.m2 = parts[3 * r + 2];
+        acc = merge(acc, m);
+    }
+    return acc;
+}
+
 // running_mean_std.py:23-30 for one feature: (mean, var) <- Chan merge with batch moments
 // (b_n, b_mean, b_m2); `cnt` is the running count BEFORE the update.  Same operation order as
 // the reference; PLB_MOMENTS_F32_FLOW reproduces numba's float32 `batch_var * batch_count`.
@@ -249,6 +332,20 @@ __device__ __forceinline__ void moments_tail(const Sums &mine, const MomentsTail
     }
     __syncthreads();
     acc = block_reduce_sums(acc, scratch);
+    if (tail.xch.peers != nullptr) {
+        // multi-GPU: hand the rank's moments to every peer; whoever consumes them waits and merges
+        if (threadIdx.x < 32) {
+            Moments m;
+            m.n = 0.0; m.mean = 0.0; m.m2 = 0.0;
+            if (threadIdx.x == 0) {
+                m = to_moments(acc);
+                tail.moments_out[0] = m.n; tail.moments_out[1] = m.mean; tail.moments_out[2] = m.m2;
+                *tail.ticket = 0u;
+            }
+            xch_push3(tail.xch, m.n, m.mean, m.m2);
+        }
+        return;
+    }
     if (threadIdx.x == 0) {
         const Moments m = to_moments(acc);
         tail.moments_out[0] = m.n;

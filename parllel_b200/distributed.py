@@ -75,6 +75,27 @@ _peer_exchanges: dict = {}
 _peer_exchange_failed = False
 
 
+def get_peer_exchange(n_vals: int, group, device) -> "PeerExchange | None":
+    """The cached peer-memory exchange for (group, n_vals), or None when symmetric memory is not
+    available / ``PLB_EXCHANGE=nccl`` is set."""
+    import os
+    global _peer_exchange_failed
+    if os.environ.get("PLB_EXCHANGE", "p2p") != "p2p" or _peer_exchange_failed:
+        return None
+    key = (id(group), int(n_vals), torch.device(device).index)
+    ex = _peer_exchanges.get(key)
+    if ex is None:
+        try:
+            ex = PeerExchange(n_vals, group, device)
+            _peer_exchanges[key] = ex
+        except Exception as err:  # symmetric memory unavailable on this system: fall back to NCCL
+            import warnings
+            warnings.warn(f"peer-memory exchange unavailable ({err!r}); using NCCL all-gather")
+            _peer_exchange_failed = True
+            return None
+    return ex
+
+
 def exchange_moments(moments: torch.Tensor, n_cols: int, layout: int, group=None) -> None:
     """In-place exchange of a rank's moments: afterwards ``moments`` holds the rank-ordered merge over
     the whole group.  Uses the peer-memory kernel when symmetric memory is available (default; set

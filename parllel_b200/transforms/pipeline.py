@@ -171,9 +171,18 @@ class FusedBatchTransforms(Transform):
         d.advantage_moments = self._moments.data_ptr() + 24
         d.workspace, d.workspace_bytes = self._ws.data_ptr(), self._ws.numel()
 
+        in_kernel_exchange = False
+        if self._distributed() and phases == _lib.PHASE_ALL and not st.staged:
+            from ..distributed import get_peer_exchange
+            ex = get_peer_exchange(3, self.group, dev)
+            if ex is not None and ex.world <= 32:
+                d.xch_peers, d.xch_rank, d.xch_world = ex.peer_table.data_ptr(), ex.rank, ex.world
+                keep.append(ex)
+                in_kernel_exchange = True
+
         def enqueue():
             s = stream_ptr(dev)
-            if self._distributed() and phases == _lib.PHASE_ALL:
+            if self._distributed() and phases == _lib.PHASE_ALL and not in_kernel_exchange:
                 _lib.check(lib.plb_batch_pipeline_f32(ctypes.byref(d), _lib.PHASE_A, s), "fused transforms (A)")
                 if nr is not None:
                     self._exchange(self._moments[0:3])
