@@ -47,6 +47,15 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def measured_traffic():
+    """dram__bytes_read + dram__bytes_write per launch of the dominant kernel, from the committed ncu capture."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            return int(json.load(f)["traffic_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 def synth_batch(seed: int, T: int = T_STEPS, B: int = B_ENVS):
     rng = np.random.default_rng(seed)
     return dict(
@@ -364,7 +373,8 @@ def main():
         "kernels_per_step": ["scan_chunked_kernel<GAE,+moments>", "elementwise_kernel<NormAdvOp>"],
         "roofline": {"bound": "hbm", "kernel": "plb::chunked::scan_chunked_kernel<MODE=GAE, HAS_STATS> (EstimateAdvantage)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "peak_source": peak_src, "traffic": None,
+                     "peak_source": peak_src, "traffic": measured_traffic(),
+                     "traffic_source": "profiles/r1_traffic.json (ncu --set full of this command; outputs still dirty in L2 at kernel end)",
                      "algorithmic_bytes_per_launch": T_STEPS * B_ENVS * GAE_BYTES_PER_TRANSITION,
                      "avg_launch_us": gae_us, "launches_timed": kernel_launches,
                      "frac_of_nominal_8TBs": achieved / 8000.0},
