@@ -171,6 +171,95 @@ def cpu_reference_arm(steps: int, warmup: int, budget_s: float, threads: int, n_
     return {"value": T_STEPS * B_all / per_step, "ms_per_step": per_step * 1e3, "steps": len(times)}
 
 
+# ----------------------------------------------------------------------------- secondary kernels
+def _graph_time_us(fn, n_inner, reps=5):
+    """Average device time of one call of `fn(i)`: `n_inner` calls captured into a CUDA graph (no host
+    gaps; CUDA events on this box tick at ~2 us), best of `reps` replays."""
+    import torch
+    for i in range(n_inner):
+        fn(i)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for i in range(n_inner):
+            fn(i)
+    g.replay()
+    torch.cuda.synchronize()
+    best = float("inf")
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1) * 1e3 / n_inner)
+    return best
+
+
+def measure_extras(dev, peak):
+    """The other BASELINE.json configs, timed on the device (inputs resident, rotating buffers > L2 where
+    the working set is smaller than L2).  Reported next to the headline, not instead of it."""
+    import torch
+
+    from parllel_b200 import ArrayDict, BatchSpec
+    from parllel_b200.replays import ReplayBuffer
+    from parllel_b200.transforms import (ClipRewards, EstimateAdvantage, FusedBatchTransforms, NormalizeAdvantage,
+                                         NormalizeObservations, NormalizeRewards)
+    out = {}
+    # C3: replay gather, ~1M-transition ring, obs 64 / act 8: 1114 algorithmic bytes per sample
+    size_T, Bn = 62464, 16
+    ring = ArrayDict({
+        "observation": torch.randn(size_T + 2, Bn, 64, device=dev)[1:-1],
+        "next_observation": torch.randn(size_T, Bn, 64, device=dev),
+        "action": torch.randn(size_T, Bn, 8, device=dev),
+        "reward": torch.randn(size_T, Bn, device=dev),
+        "terminated": torch.rand(size_T, Bn, device=dev) < 0.01})
+    for n, k in ((256, 1), (16384, 1), (256, 512)):
+        rb = ReplayBuffer(ring, BatchSpec(128, Bn), size_T=size_T, replay_batch_size=n, oldest_n_samples_invalid=1,
+                          device_rng=True)
+        rb._full, rb._cursor = True, 384
+        rb.seed(0)
+        idx = [rb.sample_indices_device(k) for _ in range(4)]
+        us = _graph_time_us(lambda i: rb.gather(idx[i % 4][0].reshape(-1), idx[i % 4][1].reshape(-1)), 8)
+        gbs = 1114 * n * k / us / 1e3
+        name = f"replay_gather_n{n}" + (f"_k{k}_fused" if k > 1 else "")
+        out[name] = {"us_per_launch": us, "GB/s": gbs, "frac_of_measured_peak": gbs / peak, "samples_per_s": n * k / us * 1e6}
+        if k == 1:
+            us_rng = _graph_time_us(lambda i: rb.sample_batch(), 8)
+            out[name]["us_sample_batch_incl_device_rng"] = us_rng
+    # C2: one NormalizeObservations step, B=1024, obs 3x84x84: 8 bytes per observation element
+    shape = (3, 84, 84)
+    obs = torch.randn((4, 1024) + shape, device=dev) * 3 + 5
+    tf = NormalizeObservations({"observation": obs}, obs_shape=shape, initial_count=10000)
+    us = _graph_time_us(lambda i: tf._step(obs[i % 4], None, dev), 8)
+    nbytes = 8 * 1024 * int(np.prod(shape))
+    out["normalize_observations_step_B1024_3x84x84"] = {"us_per_step": us, "GB/s": nbytes / us / 1e3,
+                                                        "frac_of_measured_peak": nbytes / us / 1e3 / peak,
+                                                        "transitions_per_s": 1024 / us * 1e6}
+    # full chain NormalizeRewards -> ClipRewards -> EstimateAdvantage -> NormalizeAdvantage at C1 and C4
+    for T, B in ((T_STEPS, B_ENVS), (256, 65536)):
+        n_sets = max(2, int(np.ceil(2.2 * L2_BYTES / (25 * T * B))))
+        trees = []
+        for _ in range(n_sets):
+            trees.append(ArrayDict({"reward": torch.randn(T, B, device=dev), "done": torch.rand(T, B, device=dev) < P_DONE,
+                                    "agent_info": {"value": torch.randn(T, B, device=dev)},
+                                    "bootstrap_value": torch.randn(B, device=dev),
+                                    "advantage": torch.empty(T, B, device=dev), "return_": torch.empty(T, B, device=dev),
+                                    "past_return": torch.empty(T, B, device=dev)}))
+        chain = FusedBatchTransforms([NormalizeRewards(trees[0], GAMMA), ClipRewards(-5, 5),
+                                      EstimateAdvantage(GAMMA, LAMBDA), NormalizeAdvantage(trees[0])], use_cuda_graph=False)
+        us = _graph_time_us(lambda i: chain(trees[i % n_sets]), 2 * n_sets)
+        out[f"full_chain_T{T}_B{B}"] = {"us_per_step": us, "transitions_per_s": T * B / us * 1e6,
+                                        "GB/s_on_25B_per_transition": 25 * T * B / us / 1e3,
+                                        "frac_of_measured_peak": 25 * T * B / us / 1e3 / peak}
+        ea = EstimateAdvantage(GAMMA, LAMBDA)
+        us = _graph_time_us(lambda i: ea(trees[i % n_sets]), 2 * n_sets)
+        out[f"estimate_advantage_T{T}_B{B}"] = {"us_per_launch": us, "transitions_per_s": T * B / us * 1e6,
+                                                "GB/s": 17 * T * B / us / 1e3, "frac_of_measured_peak": 17 * T * B / us / 1e3 / peak}
+        del trees
+    return out
+
+
 # ----------------------------------------------------------------------------- main
 def _debug(msg):
     if os.environ.get("PLB_BENCH_DEBUG"):
@@ -186,6 +275,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer e2e loop (0 = min(steps, 40))")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary kernels (gather, observations, full chain)")
     args = ap.parse_args()
     warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -379,6 +469,8 @@ def main():
                      "avg_launch_us": gae_us, "launches_timed": kernel_launches,
                      "frac_of_nominal_8TBs": achieved / 8000.0},
     }
+    if not distributed and not args.no_extras:
+        line["extras"] = measure_extras(dev, peak)
     if not args.no_cpu_baseline:
         res = cpu_reference_arm(steps=200, warmup=1, budget_s=12.0, threads=1)
         line["cpu_baseline"] = {"value": res["value"], "unit": UNIT, "cores": 1, "kind": "port",
