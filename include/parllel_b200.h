@@ -68,7 +68,8 @@ PLB_API const char *plb_last_error(void);
 PLB_API int plb_sm_count(void);
 /* Tuning / diagnostics knobs (process-wide; used by tools/ and the tests, not by the transforms).
  *   key 0: tile geometry of the chunked scan: 0 auto, 1 = 8 warps x 8 rows, 2 = 8 x 16, 3 = 16 x 8
- *   key 1: 1 = float32 affine maps in the chunked scan (default 0 = float64) */
+ *   key 1: 1 = float32 affine maps in the chunked scan (default 0 = float64)
+ *   key 3: NormalizeObservations step kernel: 0 auto, 1 shared-memory slab (TMA), 2 two-pass L2 slab */
 #define PLB_TUNE_CHUNK_GEOMETRY 0
 #define PLB_TUNE_CHUNK_F32 1
 PLB_API int plb_set_tuning(int key, int value);

@@ -466,10 +466,18 @@ int plb_normalize_observations_step_f32(float *obs, int64_t ld_obs, int64_t rows
     double *batch_count = reinterpret_cast<double *>(workspace);
     Moments *partials = reinterpret_cast<Moments *>(reinterpret_cast<unsigned char *>(workspace) + 64);
 
-    // single pass over HBM when a [rows x 16 columns] slab fits in shared memory
+    // 8 bytes of HBM traffic per element: a column slab is either held in shared memory (TMA in/out) or
+    // streamed twice with the second pass served by L2
     {
-        const int rc1 = obs_step_single_pass(obs, ld_obs, rows, cols, row_valid, mean, var, count, batch_count,
-                                             eps, flags, stream);
+        // measured at C2 (B = 1024, F = 21168): shared-memory slab 42 us, two-pass L2 slab 55 us, three
+        // kernels 85 us -> prefer the shared-memory slab, use the L2 variant when the slab is too tall
+        int rc1 = PLB_ERR_UNSUPPORTED;
+        const int variant = obs_variant();
+        if (variant != 2)
+            rc1 = obs_step_single_pass(obs, ld_obs, rows, cols, row_valid, mean, var, count, batch_count,
+                                       eps, flags, stream);
+        if (rc1 == PLB_ERR_UNSUPPORTED && variant != 1)
+            rc1 = obs_step_two_pass_l2(obs, ld_obs, rows, cols, row_valid, mean, var, count, batch_count, eps, flags, stream);
         if (rc1 == PLB_OK) {
             bump_count_kernel<<<1, 1, 0, stream>>>(count, batch_count);
             PLB_LAUNCH_CHECK();

@@ -206,6 +206,183 @@ obs_step_kernel(const __grid_constant__ CUtensorMap tm, const Params p)
 
 }  // namespace obs
 
+// ---------------------------------------------------------------------------------------------
+// Variant B: two passes over a [rows x 64 columns] slab, the second one served by L2.
+// Each CTA owns 256-byte-wide column slabs (full DRAM bursts, plain 128-bit loads: the TMA unit
+// tops out at ~4.4 TB/s for the 64-byte rows a shared-memory-resident slab allows at B = 1024,
+// tools/microbench/tma_width.cu).  Pass 1 streams the slab from HBM and reduces the per-column
+// moments; pass 2 re-reads it while it is still L2-resident (one CTA per SM keeps only ~40 MB of
+// slabs in flight in the 126 MB L2), normalises and stores.  HBM traffic stays 8 B per element and
+// there is no limit on the number of rows.
+// ---------------------------------------------------------------------------------------------
+namespace obs_l2 {
+
+constexpr int WCOLS = 64;              // columns per slab: 16 lanes x float4 = 256 bytes per row
+constexpr int THREADS = 256;
+constexpr int LANES = WCOLS / 4;       // 16 threads cover one row
+constexpr int GROUPS = THREADS / LANES;  // 16 row groups; thread (g, l) takes rows g, g+16, ...
+
+struct Params {
+    float *x; int64_t ld;
+    int64_t rows, cols;
+    const uint8_t *row_valid;
+    double *mean, *var;
+    const double *count;
+    double *batch_count_out;
+    double eps;
+    int flags;
+    int n_slabs;
+};
+
+__global__ void __launch_bounds__(THREADS)
+obs_step_l2_kernel(const Params p)
+{
+    __shared__ Sums part[GROUPS][WCOLS];
+    __shared__ float4 s_mu_hi[LANES], s_mu_lo[LANES], s_inv_hi[LANES], s_inv_lo[LANES];
+    const int l = threadIdx.x % LANES, g = threadIdx.x / LANES;
+    const int nrows = (int)p.rows;
+    const double cnt = p.count[0];
+    for (int s = blockIdx.x; s < p.n_slabs; s += gridDim.x) {
+        const int64_t c0 = (int64_t)s * WCOLS + 4 * l;
+        const bool col_ok = c0 < p.cols;  // cols % 4 == 0: a float4 is entirely in or out
+        float *base = p.x + c0;
+
+        // ---- pass 1: per-column moments (float32 pivot-shifted sums per run of 8 rows, float64 across runs)
+        float4 piv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (col_ok && g < nrows) piv = *reinterpret_cast<const float4 *>(base + (int64_t)g * p.ld);
+        double S1[4] = {0.0, 0.0, 0.0, 0.0}, S2[4] = {0.0, 0.0, 0.0, 0.0};
+        unsigned n_acc = 0;
+        if (col_ok) {
+            constexpr int RUN = 8;
+            for (int r0 = g; r0 < nrows; r0 += GROUPS * RUN) {
+                float4 v[RUN];
+                bool ok[RUN];
+#pragma unroll
+                for (int k = 0; k < RUN; ++k) {
+                    const int r = r0 + k * GROUPS;
+                    ok[k] = r < nrows && (p.row_valid == nullptr || p.row_valid[r] != 0);
+                    if (r < nrows) v[k] = *reinterpret_cast<const float4 *>(base + (int64_t)r * p.ld);
+                }
+                float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int k = 0; k < RUN; ++k) {
+                    if (ok[k]) {
+                        const float d0 = v[k].x - piv.x, d1 = v[k].y - piv.y, d2 = v[k].z - piv.z, d3 = v[k].w - piv.w;
+                        s1[0] += d0; s2[0] = fmaf(d0, d0, s2[0]);
+                        s1[1] += d1; s2[1] = fmaf(d1, d1, s2[1]);
+                        s1[2] += d2; s2[2] = fmaf(d2, d2, s2[2]);
+                        s1[3] += d3; s2[3] = fmaf(d3, d3, s2[3]);
+                        ++n_acc;
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { S1[q] += (double)s1[q]; S2[q] += (double)s2[q]; }
+            }
+        }
+        const float pv[4] = {piv.x, piv.y, piv.z, piv.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            Sums m;
+            m.n = (double)n_acc; m.s1 = S1[q]; m.s2 = S2[q]; m.piv = (double)pv[q];
+            part[g][4 * l + q] = m;
+        }
+        __syncthreads();
+        if (threadIdx.x < WCOLS) {
+            const int c = threadIdx.x;
+            const int64_t col = (int64_t)s * WCOLS + c;
+            Sums tot = part[0][c];
+            for (int k = 1; k < GROUPS; ++k) {
+                Sums q = part[k][c];
+                if (q.n > 0.0) {
+                    if (tot.n == 0.0) tot = q;
+                    else {
+                        q = rebase(q, tot.piv);
+                        tot.n += q.n; tot.s1 += q.s1; tot.s2 += q.s2;
+                    }
+                }
+            }
+            const Moments m = to_moments(tot);
+            double mean = 0.0, var = 1.0;
+            if (col < p.cols) {
+                mean = p.mean[col];
+                var = p.var[col];
+                chan_update_scalar(m.n, m.mean, m.m2, cnt, p.flags, mean, var);
+                p.mean[col] = mean;
+                p.var[col] = var;
+            }
+            const double inv = 1.0 / sqrt(__dadd_rn(var, p.eps));
+            const float mh = __double2float_rn(mean), ih = __double2float_rn(inv);
+            reinterpret_cast<float *>(s_mu_hi)[c] = mh;
+            reinterpret_cast<float *>(s_mu_lo)[c] = __double2float_rn(mean - (double)mh);
+            reinterpret_cast<float *>(s_inv_hi)[c] = ih;
+            reinterpret_cast<float *>(s_inv_lo)[c] = __double2float_rn(inv - (double)ih);
+            if (s == 0 && c == 0) p.batch_count_out[0] = m.n;
+        }
+        __syncthreads();
+
+        // ---- pass 2: re-read (L2), normalise with float32 hi+lo constants, store ----------------
+        if (col_ok) {
+            const float4 mh = s_mu_hi[l], ml = s_mu_lo[l], ih = s_inv_hi[l], il = s_inv_lo[l];
+            constexpr int RUN = 8;
+            for (int r0 = g; r0 < nrows; r0 += GROUPS * RUN) {
+                float4 v[RUN];
+#pragma unroll
+                for (int k = 0; k < RUN; ++k) {
+                    const int r = r0 + k * GROUPS;
+                    if (r < nrows) v[k] = *reinterpret_cast<const float4 *>(base + (int64_t)r * p.ld);
+                }
+#pragma unroll
+                for (int k = 0; k < RUN; ++k) {
+                    const int r = r0 + k * GROUPS;
+                    if (r < nrows) {
+                        float4 o;
+                        float d;
+                        d = (v[k].x - mh.x) - ml.x; o.x = fmaf(d, ih.x, d * il.x);
+                        d = (v[k].y - mh.y) - ml.y; o.y = fmaf(d, ih.y, d * il.y);
+                        d = (v[k].z - mh.z) - ml.z; o.z = fmaf(d, ih.z, d * il.z);
+                        d = (v[k].w - mh.w) - ml.w; o.w = fmaf(d, ih.w, d * il.w);
+                        *reinterpret_cast<float4 *>(base + (int64_t)r * p.ld) = o;
+                    }
+                }
+            }
+        }
+        __syncthreads();  // part[] / s_* are reused by the next slab
+    }
+}
+
+}  // namespace obs_l2
+
+static int g_obs_variant = 0;  // 0 auto, 1 shared-memory slab (TMA), 2 two-pass L2 slab
+int obs_variant() { return g_obs_variant; }
+void set_obs_variant(int v) { g_obs_variant = v; }
+
+int obs_step_two_pass_l2(float *x, int64_t ld, int64_t rows, int64_t cols, const uint8_t *row_valid,
+                         double *mean, double *var, const double *count, double *batch_count_out,
+                         double eps, int flags, cudaStream_t stream)
+{
+    using namespace obs_l2;
+    if (!(aligned(x, 16) && ld % 4 == 0 && cols % 4 == 0) || rows < 1 || rows > (int64_t)INT32_MAX / 2)
+        return PLB_ERR_UNSUPPORTED;
+    const int sms = sm_count();
+    PLB_REQUIRE(sms > 0, PLB_ERR_UNSUPPORTED, "no CUDA device");
+    Params p = {};
+    p.x = x; p.ld = ld; p.rows = rows; p.cols = cols;
+    p.row_valid = row_valid;
+    p.mean = mean; p.var = var; p.count = count;
+    p.batch_count_out = batch_count_out;
+    p.eps = eps; p.flags = flags;
+    p.n_slabs = (int)ceil_div(cols, WCOLS);
+    // keep the slabs in flight (grid x rows x 256 B) well inside L2 so that pass 2 hits
+    const int64_t slab_bytes = rows * WCOLS * 4;
+    int64_t max_ctas = (int64_t)48 * 1024 * 1024 / (slab_bytes > 0 ? slab_bytes : 1);
+    if (max_ctas < sms / 2) return PLB_ERR_UNSUPPORTED;  // slabs too tall for L2 reuse: three-kernel path
+    int grid = (int)(max_ctas < 3 * sms ? max_ctas : 3 * sms);
+    if (grid > p.n_slabs) grid = p.n_slabs;
+    obs_step_l2_kernel<<<grid, THREADS, 0, stream>>>(p);
+    PLB_LAUNCH_CHECK();
+    return PLB_OK;
+}
+
 // Returns PLB_ERR_UNSUPPORTED when the shape does not fit the single-pass design.
 int obs_step_single_pass(float *x, int64_t ld, int64_t rows, int64_t cols, const uint8_t *row_valid,
                          double *mean, double *var, const double *count, double *batch_count_out,

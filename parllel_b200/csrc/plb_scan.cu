@@ -795,6 +795,7 @@ int plb_set_tuning(int key, int value)
     switch (key) {
         case 0: plb::g_chunked_geom = value; return PLB_OK;
         case 1: plb::g_chunked_f32 = value; return PLB_OK;
+        case 3: plb::set_obs_variant(value); return PLB_OK;
         default: plb::set_error("unknown tuning key %d", key); return PLB_ERR_INVALID_ARGUMENT;
     }
 }

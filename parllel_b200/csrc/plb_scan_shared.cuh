@@ -79,6 +79,11 @@ int column_moments_partial(const float *x, int64_t ld_x, int64_t rows, int64_t c
 int column_moments(const float *x, int64_t ld_x, int64_t rows, int64_t cols, const uint8_t *row_valid,
                    double *count_out, double *mean_out, double *m2_out,
                    void *workspace, size_t workspace_bytes, cudaStream_t stream);
+int obs_variant();
+void set_obs_variant(int v);
+int obs_step_two_pass_l2(float *x, int64_t ld, int64_t rows, int64_t cols, const uint8_t *row_valid,
+                         double *mean, double *var, const double *count, double *batch_count_out,
+                         double eps, int flags, cudaStream_t stream);
 int obs_step_single_pass(float *x, int64_t ld, int64_t rows, int64_t cols, const uint8_t *row_valid,
                          double *mean, double *var, const double *count, double *batch_count_out,
                          double eps, int flags, cudaStream_t stream);

@@ -60,11 +60,13 @@ def main():
     ap.add_argument("--inner", type=int, default=1, help="launches per event pair (rotating buffer sets)")
     ap.add_argument("--rows", type=int, default=0)
     ap.add_argument("--f32", type=int, default=0)
+    ap.add_argument("--obs-variant", type=int, default=0)
     args = ap.parse_args()
     from parllel_b200 import _lib
     if args.rows:
         _lib.load().plb_set_tuning(0, args.rows)
     _lib.load().plb_set_tuning(1, args.f32)
+    _lib.load().plb_set_tuning(3, args.obs_variant)
     dev = torch.device("cuda:0")
     rng = np.random.default_rng(0)
     flush = torch.empty(256 * 2**20, dtype=torch.uint8, device=dev)  # > L2
