@@ -203,6 +203,7 @@ PLB_API int plb_normalize_observations_step_f32(
     float *obs, int64_t ld_obs, int64_t rows, int64_t cols,
     const uint8_t *row_valid,
     double *mean, double *var, double *count, double eps, int flags,
+    double clip_lo, double clip_hi, /* EXTENSION (not in the reference): clamp the normalised values; NaN = off */
     void *workspace, size_t workspace_bytes, plb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------

@@ -90,7 +90,7 @@ _SIGNATURES = {
     "plb_normalize_observations_workspace_bytes": ([c_int64, c_int64], c_size_t),
     "plb_normalize_observations_step_f32": (
         [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_int,
-         c_void_p, c_size_t, c_void_p], c_int),
+         c_double, c_double, c_void_p, c_size_t, c_void_p], c_int),
     "plb_gather_tree": (
         [ctypes.POINTER(GatherLeaf), c_int32, c_void_p, c_void_p, c_int64, c_void_p], c_int),
     "plb_replay_sample_indices": (

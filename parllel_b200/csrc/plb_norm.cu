@@ -305,7 +305,7 @@ template <int VEC>
 __global__ void __launch_bounds__(128)
 normalize_columns_kernel(float *__restrict__ x, int64_t ld_x, int64_t rows, int64_t cols,
                          const double *__restrict__ mean, const double *__restrict__ var, double eps,
-                         int64_t rows_per_split)
+                         int64_t rows_per_split, float clip_lo, float clip_hi)
 {
     const int64_t c0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
     if (c0 >= cols) return;
@@ -336,7 +336,7 @@ normalize_columns_kernel(float *__restrict__ x, int64_t ld_x, int64_t rows, int6
             if (r + u < r_hi) {
 #pragma unroll
                 for (int k = 0; k < VEC; ++k)
-                    v[u][k] = __double2float_rn(__dmul_rn(__dsub_rn((double)v[u][k], mu[k]), den[k]));
+                    v[u][k] = fminf(fmaxf(__double2float_rn(__dmul_rn(__dsub_rn((double)v[u][k], mu[k]), den[k])), clip_lo), clip_hi);
                 if (VEC == 4) {
                     float4 q;
                     q.x = v[u][0]; q.y = v[u][1 % VEC]; q.z = v[u][2 % VEC]; q.w = v[u][3 % VEC];
@@ -350,7 +350,7 @@ normalize_columns_kernel(float *__restrict__ x, int64_t ld_x, int64_t rows, int6
 }
 
 int normalize_columns(float *x, int64_t ld_x, int64_t rows, int64_t cols, const double *mean, const double *var,
-                      double eps, cudaStream_t stream)
+                      double eps, float clip_lo, float clip_hi, cudaStream_t stream)
 {
     PLB_REQUIRE(rows >= 0 && cols >= 0, PLB_ERR_INVALID_ARGUMENT, "negative extent");
     if (rows * cols == 0) return PLB_OK;
@@ -361,10 +361,10 @@ int normalize_columns(float *x, int64_t ld_x, int64_t rows, int64_t cols, const 
     const bool vec = (cols % 4 == 0) && (ld_x % 4 == 0) && aligned(x, 16);
     if (vec) {
         dim3 grid((unsigned)ceil_div(cols / 4, 128), (unsigned)splits);
-        normalize_columns_kernel<4><<<grid, 128, 0, stream>>>(x, ld_x, rows, cols, mean, var, eps, rows_per_split);
+        normalize_columns_kernel<4><<<grid, 128, 0, stream>>>(x, ld_x, rows, cols, mean, var, eps, rows_per_split, clip_lo, clip_hi);
     } else {
         dim3 grid((unsigned)ceil_div(cols, 128), (unsigned)splits);
-        normalize_columns_kernel<1><<<grid, 128, 0, stream>>>(x, ld_x, rows, cols, mean, var, eps, rows_per_split);
+        normalize_columns_kernel<1><<<grid, 128, 0, stream>>>(x, ld_x, rows, cols, mean, var, eps, rows_per_split, clip_lo, clip_hi);
     }
     PLB_LAUNCH_CHECK();
     return PLB_OK;
@@ -440,7 +440,7 @@ int plb_normalize_advantage_f32(float *advantage, int64_t ld, int64_t rows, int6
 int plb_normalize_columns_f32(float *x, int64_t ld_x, int64_t rows, int64_t cols, const double *mean,
                               const double *var, double eps, plb_stream_t stream)
 {
-    return plb::normalize_columns(x, ld_x, rows, cols, mean, var, eps, (cudaStream_t)stream);
+    return plb::normalize_columns(x, ld_x, rows, cols, mean, var, eps, -INFINITY, INFINITY, (cudaStream_t)stream);
 }
 
 size_t plb_normalize_observations_workspace_bytes(int64_t rows, int64_t cols)
@@ -451,11 +451,13 @@ size_t plb_normalize_observations_workspace_bytes(int64_t rows, int64_t cols)
 
 int plb_normalize_observations_step_f32(float *obs, int64_t ld_obs, int64_t rows, int64_t cols,
                                         const uint8_t *row_valid, double *mean, double *var, double *count,
-                                        double eps, int flags, void *workspace, size_t workspace_bytes,
-                                        plb_stream_t stream_)
+                                        double eps, int flags, double clip_lo_, double clip_hi_, void *workspace,
+                                        size_t workspace_bytes, plb_stream_t stream_)
 {
     using namespace plb;
     cudaStream_t stream = (cudaStream_t)stream_;
+    const float clip_lo = (clip_lo_ != clip_lo_) ? -INFINITY : (float)clip_lo_;
+    const float clip_hi = (clip_hi_ != clip_hi_) ? INFINITY : (float)clip_hi_;
     PLB_REQUIRE(rows >= 0 && cols >= 0, PLB_ERR_INVALID_ARGUMENT, "negative extent");
     if (cols == 0) return PLB_OK;
     PLB_REQUIRE(obs && mean && var && count, PLB_ERR_INVALID_ARGUMENT, "null pointer");
@@ -475,9 +477,10 @@ int plb_normalize_observations_step_f32(float *obs, int64_t ld_obs, int64_t rows
         const int variant = obs_variant();
         if (variant != 2)
             rc1 = obs_step_single_pass(obs, ld_obs, rows, cols, row_valid, mean, var, count, batch_count,
-                                       eps, flags, stream);
+                                       eps, flags, clip_lo, clip_hi, stream);
         if (rc1 == PLB_ERR_UNSUPPORTED && variant != 1)
-            rc1 = obs_step_two_pass_l2(obs, ld_obs, rows, cols, row_valid, mean, var, count, batch_count, eps, flags, stream);
+            rc1 = obs_step_two_pass_l2(obs, ld_obs, rows, cols, row_valid, mean, var, count, batch_count, eps, flags,
+                                       clip_lo, clip_hi, stream);
         if (rc1 == PLB_OK) {
             bump_count_kernel<<<1, 1, 0, stream>>>(count, batch_count);
             PLB_LAUNCH_CHECK();
@@ -494,7 +497,7 @@ int plb_normalize_observations_step_f32(float *obs, int64_t ld_obs, int64_t rows
     PLB_LAUNCH_CHECK();
     bump_count_kernel<<<1, 1, 0, stream>>>(count, batch_count);
     PLB_LAUNCH_CHECK();
-    return normalize_columns(obs, ld_obs, rows, cols, mean, var, eps, stream);
+    return normalize_columns(obs, ld_obs, rows, cols, mean, var, eps, clip_lo, clip_hi, stream);
 }
 
 }  // extern "C"

@@ -32,6 +32,7 @@ struct Params {
     const double *count;
     double *batch_count_out;  // workspace slot read by the count-bump kernel
     double eps;
+    float clip_lo, clip_hi;   // -inf / +inf when off
     int flags;
     int n_slabs;
     int n_boxes;              // ceil(rows / BOX_ROWS)
@@ -184,7 +185,7 @@ obs_step_kernel(const __grid_constant__ CUtensorMap tm, const Params p)
 #pragma unroll 8
         for (int r = g; r < nrows; r += GROUPS) {
             const float d = (slab[r][c] - mu_hi) - mu_lo;
-            slab[r][c] = fmaf(d, inv_hi, d * inv_lo);
+            slab[r][c] = fminf(fmaxf(fmaf(d, inv_hi, d * inv_lo), p.clip_lo), p.clip_hi);
         }
         fence_proxy_async_smem();
         __syncthreads();
@@ -230,6 +231,7 @@ struct Params {
     const double *count;
     double *batch_count_out;
     double eps;
+    float clip_lo, clip_hi;
     int flags;
     int n_slabs;
 };
@@ -337,10 +339,10 @@ obs_step_l2_kernel(const Params p)
                     if (r < nrows) {
                         float4 o;
                         float d;
-                        d = (v[k].x - mh.x) - ml.x; o.x = fmaf(d, ih.x, d * il.x);
-                        d = (v[k].y - mh.y) - ml.y; o.y = fmaf(d, ih.y, d * il.y);
-                        d = (v[k].z - mh.z) - ml.z; o.z = fmaf(d, ih.z, d * il.z);
-                        d = (v[k].w - mh.w) - ml.w; o.w = fmaf(d, ih.w, d * il.w);
+                        d = (v[k].x - mh.x) - ml.x; o.x = fminf(fmaxf(fmaf(d, ih.x, d * il.x), p.clip_lo), p.clip_hi);
+                        d = (v[k].y - mh.y) - ml.y; o.y = fminf(fmaxf(fmaf(d, ih.y, d * il.y), p.clip_lo), p.clip_hi);
+                        d = (v[k].z - mh.z) - ml.z; o.z = fminf(fmaxf(fmaf(d, ih.z, d * il.z), p.clip_lo), p.clip_hi);
+                        d = (v[k].w - mh.w) - ml.w; o.w = fminf(fmaxf(fmaf(d, ih.w, d * il.w), p.clip_lo), p.clip_hi);
                         *reinterpret_cast<float4 *>(base + (int64_t)r * p.ld) = o;
                     }
                 }
@@ -358,7 +360,7 @@ void set_obs_variant(int v) { g_obs_variant = v; }
 
 int obs_step_two_pass_l2(float *x, int64_t ld, int64_t rows, int64_t cols, const uint8_t *row_valid,
                          double *mean, double *var, const double *count, double *batch_count_out,
-                         double eps, int flags, cudaStream_t stream)
+                         double eps, int flags, float clip_lo, float clip_hi, cudaStream_t stream)
 {
     using namespace obs_l2;
     if (!(aligned(x, 16) && ld % 4 == 0 && cols % 4 == 0) || rows < 1 || rows > (int64_t)INT32_MAX / 2)
@@ -371,6 +373,7 @@ int obs_step_two_pass_l2(float *x, int64_t ld, int64_t rows, int64_t cols, const
     p.mean = mean; p.var = var; p.count = count;
     p.batch_count_out = batch_count_out;
     p.eps = eps; p.flags = flags;
+    p.clip_lo = clip_lo; p.clip_hi = clip_hi;
     p.n_slabs = (int)ceil_div(cols, WCOLS);
     // keep the slabs in flight (grid x rows x 256 B) well inside L2 so that pass 2 hits
     const int64_t slab_bytes = rows * WCOLS * 4;
@@ -386,7 +389,7 @@ int obs_step_two_pass_l2(float *x, int64_t ld, int64_t rows, int64_t cols, const
 // Returns PLB_ERR_UNSUPPORTED when the shape does not fit the single-pass design.
 int obs_step_single_pass(float *x, int64_t ld, int64_t rows, int64_t cols, const uint8_t *row_valid,
                          double *mean, double *var, const double *count, double *batch_count_out,
-                         double eps, int flags, cudaStream_t stream)
+                         double eps, int flags, float clip_lo, float clip_hi, cudaStream_t stream)
 {
     using namespace obs;
     if (!(aligned(x, 16) && ld % 4 == 0) || rows < 1 || rows > (int64_t)INT32_MAX / 2 || cols > (int64_t)INT32_MAX / 2)
@@ -412,6 +415,7 @@ int obs_step_single_pass(float *x, int64_t ld, int64_t rows, int64_t cols, const
     p.mean = mean; p.var = var; p.count = count;
     p.batch_count_out = batch_count_out;
     p.eps = eps; p.flags = flags;
+    p.clip_lo = clip_lo; p.clip_hi = clip_hi;
     p.n_slabs = (int)ceil_div(cols, FC);
     p.n_boxes = n_boxes;
     p.slab_floats = n_boxes * BOX_ROWS * FC;

@@ -83,10 +83,10 @@ int obs_variant();
 void set_obs_variant(int v);
 int obs_step_two_pass_l2(float *x, int64_t ld, int64_t rows, int64_t cols, const uint8_t *row_valid,
                          double *mean, double *var, const double *count, double *batch_count_out,
-                         double eps, int flags, cudaStream_t stream);
+                         double eps, int flags, float clip_lo, float clip_hi, cudaStream_t stream);
 int obs_step_single_pass(float *x, int64_t ld, int64_t rows, int64_t cols, const uint8_t *row_valid,
                          double *mean, double *var, const double *count, double *batch_count_out,
-                         double eps, int flags, cudaStream_t stream);
+                         double eps, int flags, float clip_lo, float clip_hi, cudaStream_t stream);
 int finalize_published_partials(void *tail_workspace, double *moments_out, cudaStream_t stream);
 int exchange_finish(const XchRef &xch, double *moments_out, double *upd_mean, double *upd_var, double *upd_count,
                     int upd_flags, cudaStream_t stream);

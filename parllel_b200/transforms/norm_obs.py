@@ -28,7 +28,8 @@ class NormalizeObservations(Transform):
     :param initial_count: seed the running statistics with this many N(0,1) samples (>= 1)
     """
 
-    def __init__(self, sample_tree, obs_shape: tuple, initial_count: float | None = None, device=None) -> None:
+    def __init__(self, sample_tree, obs_shape: tuple, initial_count: float | None = None, device=None,
+                 clip: float | None = None) -> None:
         if isinstance(sample_tree["observation"], Mapping):
             raise NotImplementedError("Dictionary observations not supported.")
         self.only_valid = "valid" in sample_tree
@@ -40,6 +41,8 @@ class NormalizeObservations(Transform):
         else:
             self.obs_statistics = RunningMeanStd(shape=self.obs_shape, device=device)
         self._ws = None
+        # EXTENSION (not in the reference): clamp the normalised observation to [-clip, clip] in the same pass
+        self.clip = clip
 
     def __call__(self, sample_tree):
         step_obs = sample_tree["observation"]
@@ -73,6 +76,8 @@ class NormalizeObservations(Transform):
             _lib.check(_lib.load().plb_normalize_columns_f32(ptr, ld, B, cols, stats.mean_tensor.data_ptr(),
                                                              stats.var_tensor.data_ptr(), EPSILON, stream_ptr(device)),
                        "plb_normalize_columns_f32")
+            if self.clip is not None:
+                obs.clamp_(-float(self.clip), float(self.clip))
             return
         lib = _lib.load()
         B = obs.shape[0]
@@ -92,5 +97,6 @@ class NormalizeObservations(Transform):
         rc = lib.plb_normalize_observations_step_f32(
             ptr, ld, B, F, vptr, stats.mean_tensor.data_ptr(), stats.var_tensor.data_ptr(),
             stats.count_tensor.data_ptr(), EPSILON, _lib.MOMENTS_F32_FLOW,
+            _lib.NAN if self.clip is None else -float(self.clip), _lib.NAN if self.clip is None else float(self.clip),
             self._ws.data_ptr(), self._ws.numel(), stream_ptr(device))
         _lib.check(rc, "NormalizeObservations")

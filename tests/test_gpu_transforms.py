@@ -403,3 +403,23 @@ def test_observation_step_kernel_variants_vs_oracle(variant, B, F, masked):
     np.testing.assert_allclose(tf.obs_statistics.var, exact.var, rtol=1e-6)
     tol = 1e-5 * max(1.0, B / 1000.0)
     np.testing.assert_allclose(d.cpu().numpy(), ref, rtol=tol, atol=tol)
+
+
+def test_observation_clip_extension():
+    """clip=c (extension) equals the reference normalisation followed by np.clip, on every kernel variant."""
+    from parllel_b200 import _lib
+    from parllel_b200.transforms import NormalizeObservations
+    rng = np.random.default_rng(0)
+    obs = (5.0 + 3.0 * rng.standard_normal((2, 96, 40))).astype(np.float32)
+    ref = obs.copy()
+    stats = O.RunningMeanStd((40,), initial_count=10)
+    for t in range(2):
+        O.normalize_observations_step(ref[t], stats)
+    ref = np.clip(ref, -1.5, 1.5)
+    for variant in (0, 1, 2):
+        _lib.load().plb_set_tuning(3, variant)
+        d = torch.from_numpy(obs).cuda()
+        NormalizeObservations({"observation": d}, obs_shape=(40,), initial_count=10, clip=1.5).normalize_batch(d)
+        _lib.load().plb_set_tuning(3, 0)
+        np.testing.assert_allclose(d.cpu().numpy(), ref, rtol=1e-5, atol=1e-5)
+        assert float(d.abs().max()) <= 1.5
