@@ -51,36 +51,52 @@ __device__ __forceinline__ uint64_t xsl_rr(u128 s)
     return (x >> rot) | (x << ((64u - rot) & 63u));
 }
 
+constexpr int WORDS_PER_THREAD = 4;                       // two consecutive 64-bit outputs per thread
+constexpr int WORDS_PER_ITER = RNG_THREADS * WORDS_PER_THREAD;
+constexpr int OUTS_PER_ITER = WORDS_PER_ITER / 2;
+
 struct RngShared {
     u128 state, inc;          // generator state at the start of the current draw
     int has;                  // buffered half-word available
     uint32_t buffered;        // the buffered half-word
-    u128 stride_mult, stride_plus;  // RNG_THREADS/2 LCG steps
-    int warp_sums[32];
-    long long last_word;      // index of the word that completed the draw
+    u128 stride_mult, stride_plus;  // OUTS_PER_ITER LCG steps
+    int warp_prefix[32];
+    int total;
+    long long last_word;      // index (in fresh words) of the word that completed the draw
 };
 
-// Exclusive prefix sum of a 0/1 flag over the CTA; returns the rank, writes the CTA total.
-__device__ __forceinline__ int block_rank(int flag, RngShared &sh, int &total)
+// Exclusive prefix sum of per-thread counts over the CTA; returns this thread's offset, CTA total in sh.total.
+__device__ __forceinline__ int block_exclusive_scan(int count, RngShared &sh)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const unsigned ballot = __ballot_sync(0xffffffffu, flag);
-    const int in_warp = __popc(ballot & ((1u << lane) - 1u));
-    if (lane == 0) sh.warp_sums[warp] = __popc(ballot);
+    int incl = count;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += v;
+    }
+    if (lane == 31) sh.warp_prefix[warp] = incl;
     __syncthreads();
-    int before = 0, all = 0;
-    for (int w = 0; w < RNG_THREADS / 32; ++w) {
-        const int c = sh.warp_sums[w];
-        if (w < warp) before += c;
-        all += c;
+    if (warp == 0) {
+        const int w = sh.warp_prefix[lane];
+        int wi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, wi, d);
+            if (lane >= d) wi += v;
+        }
+        sh.warp_prefix[lane] = wi - w;  // exclusive prefix of the warp totals
+        if (lane == 31) sh.total = wi;
     }
     __syncthreads();
-    total = all;
-    return before + in_warp;
+    const int off = sh.warp_prefix[warp] + incl - count;
+    return off;
 }
 
 // One `integers(0, high, n)` call: out[i] = (draw_i + add) % mod  (mod == 0: no post-op).
-__device__ void draw_integers(RngShared &sh, uint64_t high, long long n, int64_t *out, int64_t add, int64_t mod)
+// `skip_mult/skip_plus`: this thread's precomputed LCG jump to its first output (2*tid + 1 steps).
+__device__ void draw_integers(RngShared &sh, uint64_t high, long long n, int64_t *out, int64_t add, int64_t mod,
+                              u128 skip_mult, u128 skip_plus)
 {
     if (n <= 0) return;
     const uint32_t rng = (uint32_t)(high - 1);
@@ -91,76 +107,76 @@ __device__ void draw_integers(RngShared &sh, uint64_t high, long long n, int64_t
     const bool full_range = (rng == 0xFFFFFFFFu);
     const uint32_t rng_excl = rng + 1u;
     const uint32_t threshold = full_range ? 0u : (uint32_t)((0xFFFFFFFFu - rng) % rng_excl);
-    const u128 s0 = sh.state, inc = sh.inc;
-    const int base = sh.has;  // word 0 is the buffered half-word when present
-    __syncthreads();
-
-    // this thread's first word j = tid: output index q = (j - base) >> 1, half = (j - base) & 1
-    u128 st = 0;
-    {
-        const long long j = threadIdx.x;
-        if (j >= base) {
-            u128 m, c;
-            lcg_skip(inc, (uint64_t)(((j - base) >> 1) + 1), m, c);
-            st = m * s0 + c;
-        }
-    }
-    long long filled = 0, pos = 0;
-    while (true) {
-        const long long j = pos + threadIdx.x;
-        uint32_t w;
-        if (j < base) w = sh.buffered;
-        else {
-            const uint64_t o = xsl_rr(st);
-            w = ((j - base) & 1) ? (uint32_t)(o >> 32) : (uint32_t)o;
-        }
+    auto lemire = [&](uint32_t w, int64_t &v) -> bool {
         uint64_t m = (uint64_t)w * (uint64_t)rng_excl;
-        int accept = 1;
-        if (!full_range) {
-            const uint32_t leftover = (uint32_t)m;
-            accept = !(leftover < rng_excl && leftover < threshold);
-        } else {
-            m = (uint64_t)w << 32;
+        if (full_range) { v = (int64_t)w; return true; }
+        v = (int64_t)(m >> 32);
+        return (uint32_t)m >= threshold;
+    };
+    auto post = [&](int64_t v) -> int64_t { return mod ? (v + add) % mod : v; };
+
+    long long filled = 0;
+    // the buffered half-word (if any) is the first word of the stream
+    if (sh.has) {
+        int64_t v;
+        const bool ok = lemire(sh.buffered, v);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            sh.has = 0;
+            if (ok) out[0] = post(v);
         }
-        int total;
-        const int rank = block_rank(accept, sh, total);
+        if (ok) filled = 1;
+        __syncthreads();
+        if (filled >= n) return;
+    }
+    const u128 s0 = sh.state, inc = sh.inc;
+    // fresh words: word f (0-based) is the low (f even) / high (f odd) half of output f >> 1; this thread
+    // serves words 4*tid .. 4*tid+3 of every 4096-word block = outputs 2*tid, 2*tid+1
+    u128 st = skip_mult * s0 + skip_plus;  // state after 2*tid + 1 steps
+    long long pos = 0;                     // fresh words consumed by earlier blocks
+    while (true) {
+        const u128 st2 = st * pcg_mult() + inc;
+        const uint64_t o0 = xsl_rr(st), o1 = xsl_rr(st2);
+        const uint32_t w[4] = {(uint32_t)o0, (uint32_t)(o0 >> 32), (uint32_t)o1, (uint32_t)(o1 >> 32)};
+        int64_t v[4];
+        bool ok[4];
+        int cnt = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            ok[k] = lemire(w[k], v[k]);
+            cnt += ok[k] ? 1 : 0;
+        }
+        int rank = block_exclusive_scan(cnt, sh);
+        const int total = sh.total;
         const long long need = n - filled;
-        if (accept && rank < need) {
-            int64_t v = (int64_t)(m >> 32);
-            if (mod) v = (v + add) % mod;
-            out[filled + rank] = v;
-            if (rank == need - 1) sh.last_word = j;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (ok[k]) {
+                if (rank < need) {
+                    out[filled + rank] = post(v[k]);
+                    if (rank == need - 1) sh.last_word = pos + 4LL * threadIdx.x + k;
+                }
+                ++rank;
+            }
         }
         if (total >= need) break;
         filled += total;
-        pos += RNG_THREADS;
-        if (pos == RNG_THREADS && threadIdx.x < base) {
-            // the thread that served the buffered word joins the stream: word j = pos + tid
-            u128 mm, cc;
-            lcg_skip(inc, (uint64_t)(((pos + threadIdx.x - base) >> 1) + 1), mm, cc);
-            st = mm * s0 + cc;
-        } else {
-            st = sh.stride_mult * st + sh.stride_plus;
-        }
+        pos += WORDS_PER_ITER;
+        st = sh.stride_mult * st + sh.stride_plus;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        // words consumed from fresh outputs, outputs consumed, new buffered half-word
-        const long long words = sh.last_word + 1 - base;  // >= 0
-        if (words <= 0) {
-            sh.has = 0;  // only the buffered word was used
+        const long long words = sh.last_word + 1;            // fresh words consumed
+        const uint64_t outs = (uint64_t)((words + 1) >> 1);  // 64-bit outputs consumed
+        u128 m, c;
+        lcg_skip(inc, outs, m, c);
+        const u128 ns = m * s0 + c;
+        sh.state = ns;
+        if (words & 1) {  // the high half of the last output stays buffered
+            sh.has = 1;
+            sh.buffered = (uint32_t)(xsl_rr(ns) >> 32);
         } else {
-            const uint64_t outs = (uint64_t)((words + 1) >> 1);
-            u128 m, c;
-            lcg_skip(inc, outs, m, c);
-            const u128 ns = m * s0 + c;
-            sh.state = ns;
-            if (words & 1) {
-                sh.has = 1;
-                sh.buffered = (uint32_t)(xsl_rr(ns) >> 32);
-            } else {
-                sh.has = 0;
-            }
+            sh.has = 0;
         }
     }
     __syncthreads();
@@ -175,6 +191,159 @@ struct RngParams {
     int64_t *t_idx, *b_idx;
 };
 
+// ---------------------------------------------------------------------------------------------
+// Fast path: all 2k draws of a launch as ONE stream.  With the usual ranges a word is rejected with
+// probability < 2^-16, so the kernel speculates that every word of a 4096-word block is accepted:
+// word f then lands at output position g0 + (f - pos), which fixes its segment (minibatch, T or B)
+// and therefore its range.  The first rejected word of the block (if any) is found with a block-wide
+// minimum; everything before it is final, and the next block restarts right behind it (threads
+// re-jump the LCG only then).  Segments with a range of 1 draw nothing and are filled separately.
+// ---------------------------------------------------------------------------------------------
+struct StreamSpec {
+    uint32_t excl[2], thr[2];   // range (exclusive) and Lemire threshold of the T / B draws
+    int full_range[2];          // 1: range == 2^32, raw words
+    int draws[2];               // 0: the draw consumes no words (range 1)
+    int64_t add, mod;           // post-op of the T draw
+};
+
+__device__ void draw_stream(RngShared &sh, const RngParams &p, const StreamSpec &sp)
+{
+    __shared__ long long s_first_reject;
+    const long long n = p.n;
+    const int n_drawing = sp.draws[0] + sp.draws[1];           // word-consuming segments per minibatch
+    const long long total_out = (long long)n_drawing * n * p.k;  // outputs that consume words
+    // segments that consume nothing
+    for (int which = 0; which < 2; ++which) {
+        if (!sp.draws[which]) {
+            int64_t *dst = which == 0 ? p.t_idx : p.b_idx;
+            const int64_t v = (which == 0 && sp.mod) ? (sp.add % sp.mod) : (which == 0 ? sp.add : 0);
+            for (long long i = threadIdx.x; i < n * p.k; i += RNG_THREADS) dst[i] = v;
+        }
+    }
+    if (total_out == 0) return;
+    auto emit = [&](long long g, uint32_t w) -> bool {  // speculative position g -> (segment, index); false = rejected
+        const long long seg = g / n, idx = g - seg * n;
+        const long long mb = seg / n_drawing;
+        const int which = (n_drawing == 2) ? (int)(seg & 1) : (sp.draws[0] ? 0 : 1);
+        int64_t v;
+        if (sp.full_range[which]) v = (int64_t)w;
+        else {
+            const uint64_t m = (uint64_t)w * (uint64_t)sp.excl[which];
+            if ((uint32_t)m < sp.thr[which]) return false;
+            v = (int64_t)(m >> 32);
+        }
+        if (which == 0) {
+            if (sp.mod) v = (v + sp.add) % sp.mod;
+            p.t_idx[mb * n + idx] = v;
+        } else {
+            p.b_idx[mb * n + idx] = v;
+        }
+        return true;
+    };
+
+    long long g0 = 0;  // outputs produced so far
+    if (sh.has) {      // the buffered half-word is the first word of the stream
+        const uint32_t w = sh.buffered;
+        __syncthreads();
+        bool ok = true;
+        if (threadIdx.x == 0) {
+            sh.has = 0;
+            ok = emit(0, w);
+            sh.total = ok ? 1 : 0;
+        }
+        __syncthreads();
+        g0 = sh.total;
+        if (g0 >= total_out) return;
+    }
+    const u128 s0 = sh.state, inc = sh.inc;
+    long long pos = 0;  // fresh words consumed so far (word f = half f&1 of output f>>1)
+    bool rejump = true;
+    u128 st = 0;
+    while (true) {
+        const long long f0 = pos + 4LL * threadIdx.x;  // this thread's first word of the block
+        if (rejump) {
+            u128 m, c;
+            lcg_skip(inc, (uint64_t)(f0 >> 1) + 1ull, m, c);
+            st = m * s0 + c;
+            rejump = false;
+        }
+        const u128 st2 = st * pcg_mult() + inc;
+        const u128 st3 = st2 * pcg_mult() + inc;
+        const uint64_t o0 = xsl_rr(st), o1 = xsl_rr(st2), o2 = xsl_rr(st3);
+        uint32_t w[4];
+        if ((f0 & 1) == 0) {
+            w[0] = (uint32_t)o0; w[1] = (uint32_t)(o0 >> 32); w[2] = (uint32_t)o1; w[3] = (uint32_t)(o1 >> 32);
+        } else {
+            w[0] = (uint32_t)(o0 >> 32); w[1] = (uint32_t)o1; w[2] = (uint32_t)(o1 >> 32); w[3] = (uint32_t)o2;
+        }
+        if (threadIdx.x == 0) s_first_reject = 1LL << 62;
+        __syncthreads();
+        // pass 1: find the first word of the block that would be rejected at its speculative position
+        long long my_reject = 1LL << 62;
+#pragma unroll
+        for (int kq = 3; kq >= 0; --kq) {
+            const long long g = g0 + (f0 + kq - pos);
+            if (g < total_out) {
+                const long long seg = g / n;
+                const int which = (n_drawing == 2) ? (int)(seg & 1) : (sp.draws[0] ? 0 : 1);
+                if (!sp.full_range[which]) {
+                    const uint64_t m = (uint64_t)w[kq] * (uint64_t)sp.excl[which];
+                    if ((uint32_t)m < sp.thr[which]) my_reject = f0 + kq;
+                }
+            }
+        }
+        // warp minimum, then one atomicMin per warp that saw a rejection (rare)
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            const long long o = __shfl_xor_sync(0xffffffffu, my_reject, d);
+            my_reject = o < my_reject ? o : my_reject;
+        }
+        if ((threadIdx.x & 31) == 0 && my_reject < (1LL << 62))
+            atomicMin(reinterpret_cast<unsigned long long *>(&s_first_reject), (unsigned long long)my_reject);
+        __syncthreads();
+        const long long first_reject = s_first_reject;
+        // pass 2: everything before the first rejection (and inside the job) is final
+#pragma unroll
+        for (int kq = 0; kq < 4; ++kq) {
+            const long long f = f0 + kq;
+            const long long g = g0 + (f - pos);
+            if (f < first_reject && g < total_out) emit(g, w[kq]);
+        }
+        const long long block_end = pos + WORDS_PER_ITER;
+        const long long stop = first_reject < block_end ? first_reject : block_end;  // words [pos, stop) accepted
+        const long long produced = stop - pos;
+        if (g0 + produced >= total_out) {  // done inside this block: the last consumed word
+            pos = pos + (total_out - g0);
+            break;
+        }
+        g0 += produced;
+        if (first_reject < block_end) {
+            pos = first_reject + 1;  // the rejected word is consumed, nothing is produced for it
+            rejump = true;
+        } else {
+            pos = block_end;
+            st = sh.stride_mult * st + sh.stride_plus;
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const long long words = pos;                         // fresh words consumed
+        const uint64_t outs = (uint64_t)((words + 1) >> 1);  // 64-bit outputs consumed
+        u128 m, c;
+        lcg_skip(inc, outs, m, c);
+        const u128 ns = m * s0 + c;
+        sh.state = ns;
+        if (words & 1) {
+            sh.has = 1;
+            sh.buffered = (uint32_t)(xsl_rr(ns) >> 32);
+        } else {
+            sh.has = 0;
+        }
+    }
+    __syncthreads();
+}
+
 __global__ void __launch_bounds__(RNG_THREADS)
 replay_indices_kernel(const RngParams p)
 {
@@ -185,7 +354,7 @@ replay_indices_kernel(const RngParams p)
         sh.has = (int)(p.state[4] & 1ull);
         sh.buffered = (uint32_t)(p.state[4] >> 32);
         u128 m, c;
-        lcg_skip(sh.inc, RNG_THREADS / 2, m, c);
+        lcg_skip(sh.inc, OUTS_PER_ITER, m, c);
         sh.stride_mult = m;
         sh.stride_plus = c;
     }
@@ -200,9 +369,29 @@ replay_indices_kernel(const RngParams p)
     } else {
         high_t = (uint64_t)(p.cursor - p.newest_invalid);
     }
-    for (long long kk = 0; kk < p.k; ++kk) {
-        draw_integers(sh, high_t, p.n, p.t_idx + kk * p.n, add, mod);
-        draw_integers(sh, (uint64_t)p.B, p.n, p.b_idx + kk * p.n, 0, 0);
+    // rejection probabilities of the two draws decide between the speculative stream and the
+    // compaction path (ranges just above a power of two reject up to half of all words)
+    StreamSpec sp;
+    const uint64_t highs[2] = {high_t, (uint64_t)p.B};
+    bool rare = true;
+    for (int i = 0; i < 2; ++i) {
+        const uint32_t rng = (uint32_t)(highs[i] - 1);
+        sp.draws[i] = rng != 0u;
+        sp.full_range[i] = rng == 0xFFFFFFFFu;
+        sp.excl[i] = rng + 1u;
+        sp.thr[i] = (sp.full_range[i] || rng == 0u) ? 0u : (uint32_t)((0xFFFFFFFFu - rng) % sp.excl[i]);
+        if (sp.thr[i] > (1u << 18)) rare = false;  // > 2^-14 per word: > 1/4 expected rejection per block
+    }
+    sp.add = add; sp.mod = mod;
+    if (rare) {
+        draw_stream(sh, p, sp);
+    } else {
+        u128 skip_mult, skip_plus;
+        lcg_skip(sh.inc, 2ull * threadIdx.x + 1ull, skip_mult, skip_plus);
+        for (long long kk = 0; kk < p.k; ++kk) {
+            draw_integers(sh, high_t, p.n, p.t_idx + kk * p.n, add, mod, skip_mult, skip_plus);
+            draw_integers(sh, (uint64_t)p.B, p.n, p.b_idx + kk * p.n, 0, 0, skip_mult, skip_plus);
+        }
     }
     if (threadIdx.x == 0) {
         p.state[0] = (uint64_t)(sh.state >> 64);
