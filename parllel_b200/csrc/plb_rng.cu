@@ -221,34 +221,58 @@ __device__ void draw_stream(RngShared &sh, const RngParams &p, const StreamSpec 
         }
     }
     if (total_out == 0) return;
-    auto emit = [&](long long g, uint32_t w) -> bool {  // speculative position g -> (segment, index); false = rejected
-        const long long seg = g / n, idx = g - seg * n;
-        const long long mb = seg / n_drawing;
-        const int which = (n_drawing == 2) ? (int)(seg & 1) : (sp.draws[0] ? 0 : 1);
-        int64_t v;
-        if (sp.full_range[which]) v = (int64_t)w;
-        else {
-            const uint64_t m = (uint64_t)w * (uint64_t)sp.excl[which];
-            if ((uint32_t)m < sp.thr[which]) return false;
-            v = (int64_t)(m >> 32);
+    // position bookkeeping without per-word divisions: a cursor (minibatch, segment kind, index) is
+    // computed once per thread and block and stepped word by word
+    struct Cursor {
+        long long mb, idx;
+        int which;
+    };
+    auto locate = [&](long long g) -> Cursor {
+        Cursor c;
+        const long long seg = g / n;
+        c.idx = g - seg * n;
+        c.mb = seg / n_drawing;
+        c.which = (n_drawing == 2) ? (int)(seg & 1) : (sp.draws[0] ? 0 : 1);
+        return c;
+    };
+    auto step = [&](Cursor &c) {
+        if (++c.idx == n) {
+            c.idx = 0;
+            if (n_drawing == 2) {
+                if (c.which == 1) ++c.mb;
+                c.which ^= 1;
+            } else {
+                ++c.mb;
+            }
         }
-        if (which == 0) {
-            if (sp.mod) v = (v + sp.add) % sp.mod;
-            p.t_idx[mb * n + idx] = v;
+    };
+    auto rejected = [&](const Cursor &c, uint32_t w) -> bool {
+        if (sp.full_range[c.which]) return false;
+        return (uint32_t)((uint64_t)w * (uint64_t)sp.excl[c.which]) < sp.thr[c.which];
+    };
+    auto emit = [&](const Cursor &c, uint32_t w) {
+        int64_t v = sp.full_range[c.which] ? (int64_t)w : (int64_t)(((uint64_t)w * (uint64_t)sp.excl[c.which]) >> 32);
+        if (c.which == 0) {
+            if (sp.mod) {  // (v + add) % size_T with v < size_T and add < 2 * size_T
+                v += sp.add;
+                if (v >= sp.mod) v -= sp.mod;
+                if (v >= sp.mod) v -= sp.mod;
+            }
+            p.t_idx[c.mb * n + c.idx] = v;
         } else {
-            p.b_idx[mb * n + idx] = v;
+            p.b_idx[c.mb * n + c.idx] = v;
         }
-        return true;
     };
 
     long long g0 = 0;  // outputs produced so far
     if (sh.has) {      // the buffered half-word is the first word of the stream
         const uint32_t w = sh.buffered;
         __syncthreads();
-        bool ok = true;
         if (threadIdx.x == 0) {
             sh.has = 0;
-            ok = emit(0, w);
+            const Cursor c0 = locate(0);
+            const bool ok = !rejected(c0, w);
+            if (ok) emit(c0, w);
             sh.total = ok ? 1 : 0;
         }
         __syncthreads();
@@ -280,15 +304,15 @@ __device__ void draw_stream(RngShared &sh, const RngParams &p, const StreamSpec 
         __syncthreads();
         // pass 1: find the first word of the block that would be rejected at its speculative position
         long long my_reject = 1LL << 62;
+        const long long gbase = g0 + (f0 - pos);
+        const Cursor cur0 = locate(gbase < total_out ? gbase : 0);
+        {
+            Cursor c = cur0;
 #pragma unroll
-        for (int kq = 3; kq >= 0; --kq) {
-            const long long g = g0 + (f0 + kq - pos);
-            if (g < total_out) {
-                const long long seg = g / n;
-                const int which = (n_drawing == 2) ? (int)(seg & 1) : (sp.draws[0] ? 0 : 1);
-                if (!sp.full_range[which]) {
-                    const uint64_t m = (uint64_t)w[kq] * (uint64_t)sp.excl[which];
-                    if ((uint32_t)m < sp.thr[which]) my_reject = f0 + kq;
+            for (int kq = 0; kq < 4; ++kq) {
+                if (gbase + kq < total_out) {
+                    if (my_reject == (1LL << 62) && rejected(c, w[kq])) my_reject = f0 + kq;
+                    step(c);
                 }
             }
         }
@@ -303,11 +327,16 @@ __device__ void draw_stream(RngShared &sh, const RngParams &p, const StreamSpec 
         __syncthreads();
         const long long first_reject = s_first_reject;
         // pass 2: everything before the first rejection (and inside the job) is final
+        {
+            Cursor c = cur0;
 #pragma unroll
-        for (int kq = 0; kq < 4; ++kq) {
-            const long long f = f0 + kq;
-            const long long g = g0 + (f - pos);
-            if (f < first_reject && g < total_out) emit(g, w[kq]);
+            for (int kq = 0; kq < 4; ++kq) {
+                const long long f = f0 + kq;
+                if (f < first_reject && gbase + kq < total_out) {
+                    emit(c, w[kq]);
+                    step(c);
+                }
+            }
         }
         const long long block_end = pos + WORDS_PER_ITER;
         const long long stop = first_reject < block_end ? first_reject : block_end;  // words [pos, stop) accepted
