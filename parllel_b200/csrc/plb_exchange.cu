@@ -125,7 +125,10 @@ extern "C" {
 size_t plb_exchange_buffer_bytes(int32_t world, int64_t n_vals)
 {
     if (world < 1 || n_vals < 1) return 0;
-    return plb::EX_HEADER_BYTES + 2 * (size_t)world * (size_t)n_vals * sizeof(double);
+    const size_t generic = plb::EX_HEADER_BYTES + 2 * (size_t)world * (size_t)n_vals * sizeof(double);
+    // buffers for scalar statistics also carry the low-latency area of the in-kernel exchange
+    if (n_vals == 3) return plb::xch_total_bytes3(world);
+    return generic;
 }
 
 int plb_exchange_moments_p2p(const double *local, int64_t n_vals, void *const *peer_buffers, int32_t rank,

@@ -211,8 +211,23 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p)
     return v;
 }
 
-// Push this rank's (count, mean, M2) into slot [parity][rank] of every rank's buffer and raise the
-// flags.  Called by ONE full warp (world <= 32); lane 0 supplies the moments.
+// In-kernel exchange of one (count, mean, M2) triple per rank, low-latency ("LL") protocol: every
+// 32-bit half of the payload travels in its own naturally aligned 8-byte store {half, epoch}, so the
+// epoch tag doubles as the arrival flag -- no fence between data and flag, one NVLink store latency
+// end to end.  LL area of a rank's buffer (after the generic area of plb_exchange.cu):
+//     uint2 ll[2 (parity)][world][6]     (6 = 3 doubles x 2 halves)
+__host__ __device__ __forceinline__ size_t xch_ll_offset(int world)
+{
+    const size_t generic = XCH_HEADER_BYTES + 2 * (size_t)world * 3 * sizeof(double);
+    return (generic + 127) / 128 * 128;
+}
+__host__ __device__ __forceinline__ size_t xch_total_bytes3(int world)
+{
+    return xch_ll_offset(world) + 2 * (size_t)world * 6 * 8;
+}
+
+// Push this rank's (count, mean, M2) to every rank.  Called by ONE full warp (world <= 32); lane 0
+// supplies the moments.
 __device__ __forceinline__ void xch_push3(const XchRef &x, double n, double mean, double m2)
 {
     const int lane = threadIdx.x & 31;
@@ -229,15 +244,21 @@ __device__ __forceinline__ void xch_push3(const XchRef &x, double n, double mean
     m2 = __shfl_sync(0xffffffffu, m2, 0);
     const int par = (int)(epoch & 1u);
     if (lane < x.world) {
-        unsigned char *peer = x.peers[lane];
-        double *dst = reinterpret_cast<double *>(peer + XCH_HEADER_BYTES) + ((size_t)par * x.world + x.rank) * 3;
-        dst[0] = n; dst[1] = mean; dst[2] = m2;
-        __threadfence_system();
-        st_release_sys(reinterpret_cast<uint32_t *>(peer + 64) + par * x.world + x.rank, epoch);
+        uint2 *dst = reinterpret_cast<uint2 *>(x.peers[lane] + xch_ll_offset(x.world)) +
+                     ((size_t)par * x.world + x.rank) * 6;
+        const double vals[3] = {n, mean, m2};
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const unsigned long long bits = (unsigned long long)__double_as_longlong(vals[i]);
+            uint4 pkt;  // two 8-byte units {lo, epoch} {hi, epoch} in one 16-byte store
+            pkt.x = (uint32_t)bits; pkt.y = epoch; pkt.z = (uint32_t)(bits >> 32); pkt.w = epoch;
+            asm volatile("st.relaxed.sys.global.v4.u32 [%0], {%1, %2, %3, %4};"
+                         ::"l"(dst + 2 * i), "r"(pkt.x), "r"(pkt.y), "r"(pkt.z), "r"(pkt.w) : "memory");
+        }
     }
 }
 
-// Wait for every rank's moments of the current epoch and merge them in rank order.  Called by ONE
+// Wait for every rank's triple of the current epoch and merge them in rank order.  Called by ONE
 // full warp; every lane returns the same merged moments.
 __device__ __forceinline__ Moments xch_wait_merge3(const XchRef &x)
 {
@@ -245,20 +266,30 @@ __device__ __forceinline__ Moments xch_wait_merge3(const XchRef &x)
     const unsigned char *mine = x.peers[x.rank];
     const uint32_t epoch = *reinterpret_cast<const volatile uint32_t *>(mine);
     const int par = (int)(epoch & 1u);
+    double v[3] = {0.0, 0.0, 0.0};
     if (lane < x.world) {
-        const uint32_t *flag = reinterpret_cast<const uint32_t *>(mine + 64) + par * x.world + lane;
+        const uint2 *src = reinterpret_cast<const uint2 *>(mine + xch_ll_offset(x.world)) +
+                           ((size_t)par * x.world + lane) * 6;
         const long long t0 = clock64();
-        while (ld_acquire_sys(flag) != epoch) {
-            if (clock64() - t0 > 20000000000LL) __trap();  // a peer died: do not hang the GPU forever
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            uint32_t lo, f0, hi, f1;
+            while (true) {
+                asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(lo), "=r"(f0), "=r"(hi), "=r"(f1) : "l"(src + 2 * i) : "memory");
+                if (f0 == epoch && f1 == epoch) break;
+                if (clock64() - t0 > 20000000000LL) __trap();  // a peer died: do not hang the GPU forever
+            }
+            v[i] = __longlong_as_double((long long)(((unsigned long long)hi << 32) | (unsigned long long)lo));
         }
     }
-    __syncwarp();
-    const volatile double *parts = reinterpret_cast<const volatile double *>(mine + XCH_HEADER_BYTES) + (size_t)par * x.world * 3;
     Moments acc;
     acc.n = 0.0; acc.mean = 0.0; acc.m2 = 0.0;
-    for (int r = 0; r < x.world; ++r) {
+    for (int r = 0; r < x.world; ++r) {  // rank order, identical on every rank and lane
         Moments m;
-        m.n = parts[3 * r]; m.mean = parts[3 * r + 1]; m.m2 = parts[3 * r + 2];
+        m.n = __shfl_sync(0xffffffffu, v[0], r);
+        m.mean = __shfl_sync(0xffffffffu, v[1], r);
+        m.m2 = __shfl_sync(0xffffffffu, v[2], r);
         acc = merge(acc, m);
     }
     return acc;

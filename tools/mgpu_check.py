@@ -92,9 +92,11 @@ def main():
     big = ArrayDict({"reward": torch.randn(T2, B2, device=dev), "done": torch.rand(T2, B2, device=dev) < 0.01,
                      "agent_info": {"value": torch.randn(T2, B2, device=dev)}, "bootstrap_value": torch.randn(B2, device=dev),
                      "advantage": torch.zeros(T2, B2, device=dev), "return_": torch.zeros(T2, B2, device=dev)})
-    for mode in ("p2p", "nccl"):
+    for mode in ("none", "p2p", "nccl"):
         os.environ["PLB_EXCHANGE"] = mode
         fz = FusedBatchTransforms([EstimateAdvantage(0.99, 0.95), NormalizeAdvantage(big)])
+        if mode == "none":  # every rank on its own shard statistics: isolates host/launch contention
+            fz._distributed = lambda: False
         for _ in range(5):
             fz(big)
         torch.cuda.synchronize(); dist.barrier()
@@ -106,6 +108,26 @@ def main():
         if rank == 0:
             print(f"sharded step (C1 per GPU, world {world}) with {mode} exchange: {e0.elapsed_time(e1) / 500 * 1e3:.1f} us")
         fz._graphs.clear(); fz._bound.clear()
+    # latency of the stand-alone exchange kernel (all ranks ping each other back to back)
+    from parllel_b200.distributed import PeerExchange
+    ex = PeerExchange(3, None, dev)
+    loc = torch.tensor([1.0 + rank, 2.0, 3.0], dtype=torch.float64, device=dev)
+    out = torch.zeros(3, dtype=torch.float64, device=dev)
+    for _ in range(10):
+        ex.exchange(loc, out, 0, 1)
+    torch.cuda.synchronize(); dist.barrier()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(100):
+            ex.exchange(loc, out, 0, 1)
+    g.replay(); torch.cuda.synchronize(); dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        g.replay()
+    e1.record(); torch.cuda.synchronize()
+    if rank == 0:
+        print(f"stand-alone peer-memory exchange, world {world}: {e0.elapsed_time(e1) / 1000 * 1e3:.2f} us per exchange (kernel launch included)")
     if rank == 0:
         print("mgpu_check OK")
     torch.cuda.synchronize()
