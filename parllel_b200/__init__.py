@@ -8,7 +8,7 @@ hand-written CUDA kernels behind the C ABI of ``include/parllel_b200.h``.
 """
 from .arrays import DeviceArray
 from .tree import ArrayDict, dict_map
-from .types import BatchSpec
+from .spec import BatchSpec
 
 __all__ = ["ArrayDict", "BatchSpec", "DeviceArray", "dict_map"]
 __version__ = "0.1.0"

@@ -1,5 +1,8 @@
-"""B200-native drop-ins for parllel's replay containers (parllel/replays/__init__.py)."""
-from .batched_dataloader import BatchedDataLoader
-from .replay import ReplayBuffer
+"""Minibatch sources of the algorithms, B200-native: the SAC replay ring (``ReplayBuffer``) and PPO's
+shuffled epoch loader (``BatchedDataLoader``), both gathering with one CUDA launch over all leaves."""
+from . import batched_dataloader as _loader, replay as _replay
+
+ReplayBuffer = _replay.ReplayBuffer
+BatchedDataLoader = _loader.BatchedDataLoader
 
 __all__ = ["BatchedDataLoader", "ReplayBuffer"]

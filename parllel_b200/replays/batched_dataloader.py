@@ -19,7 +19,7 @@ from .. import _lib
 from .._leaves import default_device, stream_ptr
 from ..arrays import DeviceArray
 from ..tree import ArrayDict
-from ..types import BatchSpec
+from ..spec import BatchSpec
 from .replay import _flatten, _unflatten
 
 

@@ -25,7 +25,7 @@ from .. import _lib
 from .._leaves import default_device, stream_ptr
 from ..arrays import DeviceArray
 from ..tree import ArrayDict
-from ..types import BatchSpec
+from ..spec import BatchSpec
 
 
 def _flatten(tree, prefix=()):

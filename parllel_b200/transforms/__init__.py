@@ -1,22 +1,21 @@
-"""B200-native drop-ins for parllel's batch transforms (parllel/transforms/__init__.py)."""
-from .advantage import EstimateAdvantage
-from .clip_rewards import ClipRewards
-from .multi_advantage import EstimateMultiAgentAdvantage
-from .norm_advantage import NormalizeAdvantage
-from .norm_obs import NormalizeObservations
-from .norm_rewards import NormalizeRewards
-from .pipeline import FusedBatchTransforms
-from .running_mean_std import RunningMeanStd
-from .transform import Transform
+"""Batch post-processing operators of parllel, B200-native.
 
-__all__ = [
-    "EstimateAdvantage",
-    "EstimateMultiAgentAdvantage",
-    "FusedBatchTransforms",
-    "ClipRewards",
-    "NormalizeAdvantage",
-    "NormalizeObservations",
-    "NormalizeRewards",
-    "RunningMeanStd",
-    "Transform",
-]
+The public names match ``parllel.transforms`` so scripts only change the import path; two names are
+additions: ``FusedBatchTransforms`` (runs a sampler's transform list as one fused chain) and the
+device-resident ``RunningMeanStd``.
+"""
+from . import (advantage as _advantage, base as _base, clip_rewards as _clip, multi_advantage as _multi,
+               norm_advantage as _norm_adv, norm_obs as _norm_obs, norm_rewards as _norm_rew,
+               pipeline as _pipeline, running_mean_std as _rms)
+
+Transform = _base.Transform
+EstimateAdvantage = _advantage.EstimateAdvantage
+EstimateMultiAgentAdvantage = _multi.EstimateMultiAgentAdvantage
+NormalizeAdvantage = _norm_adv.NormalizeAdvantage
+NormalizeObservations = _norm_obs.NormalizeObservations
+NormalizeRewards = _norm_rew.NormalizeRewards
+ClipRewards = _clip.ClipRewards
+RunningMeanStd = _rms.RunningMeanStd
+FusedBatchTransforms = _pipeline.FusedBatchTransforms
+
+__all__ = sorted(name for name, obj in globals().items() if isinstance(obj, type) and not name.startswith("_"))

@@ -7,7 +7,7 @@ from __future__ import annotations
 
 from .. import _lib
 from .._leaves import Staging, batch_rank, is_array_leaf, rows_2d, stream_ptr
-from .transform import Transform
+from .base import Transform
 
 
 class EstimateAdvantage(Transform):

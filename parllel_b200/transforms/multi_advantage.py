@@ -19,7 +19,7 @@ import torch
 
 from .. import _lib
 from .._leaves import Staging, is_array_leaf, rows_2d, stream_ptr
-from .transform import Transform
+from .base import Transform
 
 
 class ProblemType(Enum):

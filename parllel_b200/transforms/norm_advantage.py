@@ -5,7 +5,7 @@ import torch
 
 from .. import _lib
 from .._leaves import Staging, batch_rank, is_array_leaf, rows_2d, stream_ptr
-from .transform import Transform
+from .base import Transform
 
 EPSILON = 1e-6
 

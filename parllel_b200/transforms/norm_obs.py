@@ -9,7 +9,7 @@ import torch
 from .. import _lib
 from .._leaves import Staging, is_array_leaf, rows_2d, stream_ptr
 from .running_mean_std import RunningMeanStd
-from .transform import Transform
+from .base import Transform
 
 EPSILON = 1e-6
 

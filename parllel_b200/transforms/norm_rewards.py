@@ -8,7 +8,7 @@ import torch
 from .. import _lib
 from .._leaves import Staging, batch_rank, is_array_leaf, previous_row, rows_2d, stream_ptr
 from .running_mean_std import RunningMeanStd
-from .transform import Transform
+from .base import Transform
 
 EPSILON = 1e-6
 

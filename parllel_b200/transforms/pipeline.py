@@ -29,7 +29,7 @@ from .norm_advantage import EPSILON as ADV_EPSILON
 from .norm_advantage import NormalizeAdvantage
 from .norm_rewards import EPSILON as REWARD_EPSILON
 from .norm_rewards import NormalizeRewards
-from .transform import Transform
+from .base import Transform
 
 _ORDER = (NormalizeRewards, ClipRewards, EstimateAdvantage, NormalizeAdvantage)
 
