@@ -423,3 +423,94 @@ def test_observation_clip_extension():
         _lib.load().plb_set_tuning(3, 0)
         np.testing.assert_allclose(d.cpu().numpy(), ref, rtol=1e-5, atol=1e-5)
         assert float(d.abs().max()) <= 1.5
+
+
+class _HostPaddedArray:
+    """Stand-in for a parllel ``Array`` on the host (numpy base with leading padding rows, window view
+    through ``__array__``, ``arr[-1]`` addressing the padding row before the window, ``rotate()``):
+    what the drop-in path duck-types on when the real class is not importable (GPU box)."""
+
+    def __init__(self, T, B, dtype, padding):
+        self.padding, self._T = padding, T
+        self._base = np.zeros((T + 2 * padding, B), dtype)
+
+    @property
+    def shape(self):
+        return (self._T,) + self._base.shape[1:]
+
+    batch_shape = shape
+
+    def __array__(self, dtype=None, copy=None):
+        return self._base[self.padding: self.padding + self._T]
+
+    def __getitem__(self, i):
+        assert isinstance(i, int)
+        out = _HostPaddedArray.__new__(_HostPaddedArray)
+        out.padding, out._T, out._base = 0, 1, self._base[self.padding + i][None]
+        out.__class__ = _HostRow
+        return out
+
+    def __setitem__(self, key, value):
+        np.asarray(self)[key] = value
+
+    def rotate(self):
+        p = self.padding
+        if p:
+            self._base[0: 2 * p] = self._base[self._T: self._T + 2 * p].copy()
+
+
+class _HostRow(_HostPaddedArray):
+    def __array__(self, dtype=None, copy=None):
+        return self._base[0]
+
+    @property
+    def shape(self):
+        return self._base.shape[1:]
+
+
+def test_host_array_leaves_with_padding_rows(golden):
+    """Drop-in path on host leaves that carry parllel's padding semantics: the carry rows
+    (past_return[-1], done[-1]) are read from the padding, results are written back in place."""
+    from parllel_b200 import ArrayDict
+    from parllel_b200.transforms import ClipRewards, EstimateAdvantage, NormalizeAdvantage, NormalizeRewards
+    g = golden("pipeline_c0")
+    T, B, p_done, n_batches, with_valid, lam, clip_lo, clip_hi, init_count = g["meta"]
+    T, B = int(T), int(B)
+    tree = ArrayDict({
+        "reward": _HostPaddedArray(T, B, np.float32, 0), "done": _HostPaddedArray(T, B, np.bool_, 1),
+        "agent_info": {"value": _HostPaddedArray(T, B, np.float32, 0)},
+        "bootstrap_value": np.zeros(B, np.float32),
+        "advantage": _HostPaddedArray(T, B, np.float32, 0), "return_": _HostPaddedArray(T, B, np.float32, 0),
+        "past_return": _HostPaddedArray(T, B, np.float32, 1)})
+    tfs = [NormalizeRewards(tree, discount=0.99), ClipRewards(clip_lo, clip_hi), EstimateAdvantage(0.99, lam),
+           NormalizeAdvantage(tree)]
+    for it in range(int(n_batches)):
+        for k in ("reward", "done", "advantage", "return_", "past_return"):
+            tree[k].rotate()
+        tree["reward"][...] = g[f"b{it}_in_reward"]
+        tree["done"][...] = g[f"b{it}_in_done"]
+        tree["agent_info"]["value"][...] = g[f"b{it}_in_value"]
+        tree["bootstrap_value"][...] = g[f"b{it}_in_bootstrap_value"]
+        for tf in tfs:
+            assert tf(tree) is tree
+        for k in ("past_return", "reward", "return_", "advantage"):
+            assert_within_tolerance(np.asarray(tree[k]), g[f"b{it}_out_{k}"], what=f"batch {it} {k}")
+
+
+def test_zero_extent_calls_are_noops():
+    """Empty inputs: every entry point returns success without touching memory."""
+    from parllel_b200 import _lib
+    lib = _lib.load()
+    ws = torch.zeros(lib.plb_batch_moments_workspace_bytes(), dtype=torch.uint8, device="cuda")
+    out = torch.full((3,), -1.0, dtype=torch.float64, device="cuda")
+    s = torch.cuda.current_stream().cuda_stream
+    assert lib.plb_compute_discount_return_f32(0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 8, 0, 1, 0.99, 0, s) == 0
+    assert lib.plb_compute_past_discount_return_f32(0, 0, 0, 0, 0, 0, 0, 0, 0, 4, 0.99, 0, s) == 0
+    assert lib.plb_scale_clip_f32(0, 0, 0, 7, 0, 1e-6, -1.0, 1.0, s) == 0
+    assert lib.plb_normalize_advantage_f32(0, 0, 5, 0, 1, out.data_ptr(), 1e-6, s) == 0
+    assert lib.plb_normalize_columns_f32(0, 0, 0, 9, 0, 0, 1e-6, s) == 0
+    assert lib.plb_gather_tree(None, 0, 0, 0, 0, s) == 0
+    assert lib.plb_replay_sample_indices(out.data_ptr(), 8, 2, 3, 0, 0, 0, 0, 1, out.data_ptr(), out.data_ptr(), s) == 0
+    # moments of an empty region: count 0 (mean/M2 0), workspace left reusable
+    _lib.check(lib.plb_batch_moments_f32(0, 0, 0, 0, 0, 0, out.data_ptr(), ws.data_ptr(), ws.numel(), s))
+    assert out.cpu().tolist() == [0.0, 0.0, 0.0]
