@@ -357,16 +357,17 @@ def main():
         elapsed_ms = ev0.elapsed_time(ev1)
         _debug("timed region done")
 
-        # dominant kernel alone (phase B of the same chain = the GAE scan with fused advantage moments):
+        # dominant kernel alone, configured as inside the timed step (phase B publishing per-CTA partials = the
+        # GAE scan with fused advantage moments):
         # one launch per buffer set captured into a CUDA graph, replayed until `steps` launches have run
         raw = FusedBatchTransforms([EstimateAdvantage(GAMMA, LAMBDA), NormalizeAdvantage(sets[0])], use_cuda_graph=False)
         for i in range(n_sets):
-            raw(sets[i], phases=_lib.PHASE_B)
+            raw(sets[i], phases=_lib.PHASE_B | _lib.PHASE_PARTIALS)
         torch.cuda.synchronize()
         kgraph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(kgraph):
             for i in range(n_sets):
-                raw(sets[i], phases=_lib.PHASE_B)
+                raw(sets[i], phases=_lib.PHASE_B | _lib.PHASE_PARTIALS)
         kgraph.replay()
         torch.cuda.synchronize()
         n_replays = max(1, args.steps // n_sets)
@@ -460,8 +461,9 @@ def main():
                 "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
                 "api": "HostBatchPipeline(FusedBatchTransforms([EstimateAdvantage, NormalizeAdvantage])).submit(tree)/wait() on pinned numpy trees, 2 slots"},
         "gpu_launches": args.steps * 2,
-        "kernels_per_step": ["scan_chunked_kernel<GAE,+moments>", "elementwise_kernel<NormAdvOp>"],
-        "roofline": {"bound": "hbm", "kernel": "plb::chunked::scan_chunked_kernel<MODE=GAE, HAS_STATS> (EstimateAdvantage)",
+        "kernels_per_step": ["scan_pipelined_kernel<GAE,+moments>", "normalize_advantage_partials_kernel"] if world == 1 else
+                            ["scan_pipelined_kernel<GAE,+moments,+NVLink push>", "normalize_advantage_xch_kernel"],
+        "roofline": {"bound": "hbm", "kernel": "plb::chunked::scan_pipelined_kernel<MODE=GAE, HAS_STATS> (EstimateAdvantage + fused advantage moments, per-CTA partials as in the step)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "peak_source": peak_src, "traffic": measured_traffic(),
                      "traffic_source": "profiles/r1_traffic.json (ncu --set full of this command; outputs still dirty in L2 at kernel end)",

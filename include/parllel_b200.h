@@ -72,6 +72,7 @@ PLB_API int plb_sm_count(void);
  *   key 3: NormalizeObservations step kernel: 0 auto, 1 shared-memory slab (TMA), 2 two-pass L2 slab */
 #define PLB_TUNE_CHUNK_GEOMETRY 0
 #define PLB_TUNE_CHUNK_F32 1
+#define PLB_TUNE_SCAN_PIPELINED 4   /* 1 (default): software-pipelined tile loop; 0: two-phase loop */
 PLB_API int plb_set_tuning(int key, int value);
 
 /* ------------------------------------------------------------------------------------
@@ -254,6 +255,10 @@ PLB_API int plb_replay_sample_indices(
 #define PLB_PHASE_B 2 /* update running stats; advantage scan (+scale/clip, +advantage moments) */
 #define PLB_PHASE_C 4 /* normalise advantage                                  */
 #define PLB_PHASE_ALL 7
+/* modifier for single-GPU callers that issue B and C as separate calls on the same descriptor and
+ * workspace: the advantage statistics travel as the scan's per-CTA partial sums (no serial last-CTA
+ * reduction in the scan; `advantage_moments` is written by the C call) -- pass it to both calls */
+#define PLB_PHASE_PARTIALS 8
 
 typedef struct {
     int64_t T, B;

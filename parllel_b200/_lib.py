@@ -54,6 +54,7 @@ class BatchPipeline(ctypes.Structure):
 
 
 PHASE_A, PHASE_B, PHASE_C, PHASE_ALL = 1, 2, 4, 7
+PHASE_PARTIALS = 8  # modifier: B and C issued by separate calls, statistics travel as per-CTA partials
 
 _SIGNATURES = {
     "plb_version": ([], c_int),

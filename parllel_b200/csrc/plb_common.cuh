@@ -167,6 +167,37 @@ __device__ __forceinline__ Sums block_reduce_sums(Sums a, Sums *scratch)
     return a;
 }
 
+// Cheaper variant for callers whose pivot is already uniform within each warp: plain shuffle adds,
+// one barrier, then thread 0 rebases the (<= 32) warp totals in warp order.  Result valid in thread 0.
+__device__ __forceinline__ Sums block_reduce_sums_warp_pivot(Sums a, Sums *scratch)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nwarps = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        a.n += __shfl_down_sync(0xffffffffu, a.n, d);
+        a.s1 += __shfl_down_sync(0xffffffffu, a.s1, d);
+        a.s2 += __shfl_down_sync(0xffffffffu, a.s2, d);
+    }
+    if (lane == 0) scratch[warp] = a;
+    __syncthreads();
+    Sums acc;
+    acc.n = 0.0; acc.s1 = 0.0; acc.s2 = 0.0; acc.piv = 0.0;
+    if (threadIdx.x == 0) {
+        for (int w = 0; w < nwarps; ++w) {
+            Sums q = scratch[w];
+            if (q.n > 0.0) {
+                if (acc.n == 0.0) acc = q;
+                else {
+                    q = rebase(q, acc.piv);
+                    acc.n += q.n; acc.s1 += q.s1; acc.s2 += q.s2;
+                }
+            }
+        }
+    }
+    return acc;
+}
+
 __device__ __forceinline__ bool is_nan_bound(double b) { return b != b; }
 #endif
 

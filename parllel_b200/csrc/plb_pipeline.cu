@@ -42,11 +42,17 @@ static int run_pipeline(const plb_batch_pipeline *d, int phases, cudaStream_t st
     unsigned char *ws = reinterpret_cast<unsigned char *>(d->workspace);
     void *ws_a = ws, *ws_b = ws + MOMENTS_WS_BYTES;
     int rc;
+    // PLB_PHASE_PARTIALS: phases B and C are issued by separate calls on one GPU and the advantage
+    // statistics travel between them as the scan's per-CTA partial sums (as in a PLB_PHASE_ALL call)
+    const bool split_partials = (phases & PLB_PHASE_PARTIALS) != 0;
+    phases &= ~PLB_PHASE_PARTIALS;
+    PLB_REQUIRE(!split_partials || !(d->xch_peers != nullptr && d->xch_world > 1), PLB_ERR_INVALID_ARGUMENT,
+                "PLB_PHASE_PARTIALS is a single-GPU mode");
     // whole chain in one call on one GPU: the advantage scan only publishes per-CTA partial sums and
     // the normalise kernel reduces them in its prologue (no serial last-CTA epilogue in the scan)
-    const bool direct_partials = (phases == PLB_PHASE_ALL) && est_adv && norm_adv && (T * B) % 4 == 0 &&
+    const bool direct_partials = (phases == PLB_PHASE_ALL || split_partials) && est_adv && norm_adv && (T * B) % 4 == 0 &&
                                  !(d->xch_peers != nullptr && d->xch_world > 1);
-    bool adv_partials_published = false;
+    bool adv_partials_published = direct_partials && split_partials && !(phases & PLB_PHASE_B);
     // same idea for the reward statistics: on one GPU the CTA that finishes the past-return moments
     // also applies update_from_moments to the running state (no separate update launch)
     // multi-GPU: exchange both statistics inside the kernels over peer memory

@@ -214,6 +214,7 @@ struct Params {
     // optional fused moments of out0
     const uint8_t *valid; int64_t ld_valid;
     MomentsTail tail;
+    int debug;                    // experiments only (plb_set_tuning key 5): 1 = skip the in-loop sums, 2 = skip the tail
 };
 
 struct TensorMaps {
@@ -402,8 +403,8 @@ scan_chunked_kernel(const __grid_constant__ TensorMaps tm, const Params p)
                 sh->aggC[par][warp][lane] = c;
             }
 
-            // outs[par] was last stored two tiles ago: make sure that TMA store has read it
-            if (threadIdx.x == 0) tma_store_wait_read<1>();
+            // outs[par] was handed to the TMA one iteration back (tile k-2): it must have been read
+            if (threadIdx.x == 0) tma_store_wait_read<0>();
             __syncthreads();  // stage fully read; aggregates visible; outs[par ^ 1] complete; outs[par] free
 
             if (threadIdx.x == 0) {
@@ -455,8 +456,8 @@ scan_chunked_kernel(const __grid_constant__ TensorMaps tm, const Params p)
                 if (HAS_STATS) ystat[u] = y0;
             }
             if (HAS_STATS) {
-                if (!st_has) {  // pivot: any value of the data's magnitude will do
-                    st_piv = ystat[0];
+                if (!st_has) {  // pivot: any value of the data's magnitude will do (uniform within the warp)
+                    st_piv = __shfl_sync(0xffffffffu, ystat[0], 0);
                     st_has = true;
                 }
                 if (stats_fast) {
@@ -497,9 +498,328 @@ scan_chunked_kernel(const __grid_constant__ TensorMaps tm, const Params p)
     if (HAS_STATS) {  // the grid reduction overlaps the drain of the last stores
         Sums acc;
         acc.n = (double)st_n; acc.s1 = st_s1; acc.s2 = st_s2; acc.piv = (double)st_piv;
-        moments_tail(acc, p.tail, red_scratch);
+        moments_tail<true>(acc, p.tail, red_scratch);
     }
     // smem must stay alive (and the global writes complete) before the CTA retires
+    if (threadIdx.x == 0) tma_store_wait<0>();
+}
+
+
+// ---------------------------------------------------------------------------------
+// Software-pipelined variant (default).  Same tiles, shared-memory layout and numerics as
+// scan_chunked_kernel, but the two register passes of consecutive tiles are fused: between two CTA
+// barriers every warp finalises tile j (independent FMAs + staging stores) while it scans tile j+1
+// (the dependent chain), row by row in one unrolled loop, so the chain's latency hides behind the
+// independent work instead of being exposed twice per tile.  The aggregates of the warps are
+// fetched with independent shared-memory loads before the (predicated) compose chain.
+// ---------------------------------------------------------------------------------
+template <int MODE, typename ACC, int NW, int R, bool HAS_PRE, bool HAS_STATS>
+__global__ void __launch_bounds__(NW * 32)
+scan_pipelined_kernel(const __grid_constant__ TensorMaps tm, const Params p)
+{
+    constexpr int TC = NW * R;
+    constexpr bool REVERSE = (MODE != 2);
+    constexpr int N_OUT = (REVERSE ? 2 : 1) + (HAS_PRE ? 1 : 0);
+    constexpr int PRE_SLOT = N_OUT - 1;
+    constexpr uint32_t TX_BYTES = REVERSE ? (sizeof(float) * TC * W * 2 + TC * W) : (sizeof(float) * TC * W + TC * W);
+    using StageT = Stage<TC>;
+    using OutT = OutTile<TC, N_OUT>;
+    using SharedT = Shared<ACC, NW>;
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    StageT *stages = reinterpret_cast<StageT *>(smem_raw);
+    OutT *outs = reinterpret_cast<OutT *>(smem_raw + sizeof(StageT) * p.n_stages);
+    SharedT *sh = reinterpret_cast<SharedT *>(smem_raw + sizeof(StageT) * p.n_stages + 2 * sizeof(OutT));
+    __shared__ Sums red_scratch[32];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_stages = p.n_stages, n_chunks = p.n_chunks, n_strips = p.n_strips;
+    const int64_t T = p.T;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < n_stages; ++s) mbar_init(&sh->full[s], 1);
+        fence_proxy_async_smem();
+    }
+    __syncthreads();
+
+    // ---- producer state (thread 0 only) -------------------------------------------------
+    int iss_strip = blockIdx.x, iss_chunk = 0, iss_stage = 0;
+    auto issue_one = [&]() {
+        const int c0 = iss_strip * W;
+        const int t0 = REVERSE ? (int)T - (iss_chunk + 1) * TC : iss_chunk * TC;
+        unsigned long long *bar = &sh->full[iss_stage];
+        StageT &S = stages[iss_stage];
+        mbar_arrive_expect_tx(bar, TX_BYTES);
+        tma_load_2d(&S.r[0][0], &tm.r, c0, t0, bar);
+        if (REVERSE) {
+            tma_load_2d(&S.v[0][0], &tm.v, c0, t0, bar);
+            tma_load_2d(&S.d[0][0], &tm.d, c0, t0, bar);
+        } else {
+            tma_load_2d(&S.d[0][0], &tm.d, c0, t0 - 1, bar);  // done[t-1]
+        }
+        if (++iss_chunk == n_chunks) { iss_chunk = 0; iss_strip += gridDim.x; }
+        if (++iss_stage == n_stages) iss_stage = 0;
+    };
+    // ---- store state (thread 0 only) ----------------------------------------------------
+    bool st_pending = false;
+    int st_c0 = 0, st_t0 = 0;
+    auto store_tile = [&](int buf) {
+        if (REVERSE && st_t0 < 0) {
+            const int skip = -st_t0;
+            tma_store_2d(&tm.o0_rag, &outs[buf].o[0][skip][0], st_c0, 0);
+            tma_store_2d(&tm.o1_rag, &outs[buf].o[1][skip][0], st_c0, 0);
+            if (HAS_PRE) tma_store_2d(&tm.o2_rag, &outs[buf].o[PRE_SLOT][skip][0], st_c0, 0);
+        } else {
+            tma_store_2d(&tm.o0, &outs[buf].o[0][0][0], st_c0, st_t0);
+            if (REVERSE) tma_store_2d(&tm.o1, &outs[buf].o[1][0][0], st_c0, st_t0);
+            if (HAS_PRE) tma_store_2d(&tm.o2, &outs[buf].o[PRE_SLOT][0][0], st_c0, st_t0);
+        }
+        tma_store_commit();
+    };
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tm.r);
+        if (REVERSE) tma_prefetch_desc(&tm.v);
+        tma_prefetch_desc(&tm.d);
+        for (int s = 0; s < n_stages && iss_strip < n_strips; ++s) issue_one();
+        tma_prefetch_desc(&tm.o0);
+        if (REVERSE) tma_prefetch_desc(&tm.o1);
+        if (HAS_PRE) tma_prefetch_desc(&tm.o2);
+    }
+
+    const ACC gamma = (ACC)p.gamma;
+    const ACC gl = (ACC)(p.gamma * p.lambda);
+    double inv_denom = 1.0;
+    float clip_lo = 0.f, clip_hi = 0.f;
+    if (HAS_PRE) {
+        if (p.reward_var != nullptr) inv_denom = 1.0 / sqrt(*p.reward_var + p.reward_eps);
+        clip_lo = p.clip_lo;
+        clip_hi = p.clip_hi;
+    }
+
+    float st_piv = 0.f;
+    bool st_has = false;
+    double st_s1 = 0.0, st_s2 = 0.0;
+    unsigned st_n = 0;
+
+    const int i0 = warp * R;
+    const int n_my_strips = blockIdx.x < n_strips ? (n_strips - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const int n_tiles = n_my_strips * n_chunks;
+
+    // register state of the tile between its two passes
+    ACC A[R], C[R];
+    float vreg[R], rpre[HAS_PRE ? R : 1];
+    (void)vreg; (void)rpre;
+#pragma unroll
+    for (int u = 0; u < R; ++u) { A[u] = (ACC)0; C[u] = (ACC)0; vreg[u] = 0.f; }
+
+    // cursor of the tile being scanned (pass 1) and of the tile being finalised (pass 2)
+    int nx_strip = blockIdx.x, nx_k = 0;
+    int cu_strip = 0, cu_k = 0;
+    ACC nx_carry0 = (ACC)0, cu_carry0 = (ACC)0;
+    int stage = 0, par = 0;  // input stage and staging/aggregate parity of the tile being scanned
+    uint32_t phase = 0;
+
+    auto body = [&](auto p2_tag, auto p1_tag) {
+        constexpr bool P2 = decltype(p2_tag)::value, P1 = decltype(p1_tag)::value;
+        const int pc = par ^ 1;  // parity of the tile being finalised
+        ACC cin = (ACC)0;
+        int64_t cu_t0 = 0;
+        if (P2) {
+            cu_t0 = REVERSE ? T - (int64_t)(cu_k + 1) * TC : (int64_t)cu_k * TC;
+            // outs[pc] was handed to the TMA two tiles ago (store issued one iteration back): it must
+            // have been read before this iteration overwrites it
+            if (threadIdx.x == 0) tma_store_wait_read<0>();
+            __syncthreads();  // aggregates of this tile visible; its input stage fully read; outs[par] complete
+            if (threadIdx.x == 0) {
+                if (iss_strip < n_strips) issue_one();
+                if (st_pending) store_tile(par);
+                st_pending = true;
+                st_c0 = cu_strip * W;
+                st_t0 = (int)cu_t0;
+            }
+            ACC aC[NW - 1], aA[NW - 1];
+            if (REVERSE) {
+#pragma unroll
+                for (int w = 1; w < NW; ++w) { aC[w - 1] = sh->aggC[pc][w][lane]; aA[w - 1] = sh->aggA[pc][w][lane]; }
+            } else {
+#pragma unroll
+                for (int w = 0; w < NW - 1; ++w) { aC[w] = sh->aggC[pc][w][lane]; aA[w] = sh->aggA[pc][w][lane]; }
+            }
+            cin = (cu_k == 0) ? cu_carry0 : sh->carry[pc ^ 1][lane];
+            if (REVERSE) {
+#pragma unroll
+                for (int w = NW - 1; w >= 1; --w) if (w > warp) cin = fma(aC[w - 1], cin, aA[w - 1]);
+                if (warp == 0) sh->carry[pc][lane] = fma(C[0], cin, A[0]);
+            } else {
+#pragma unroll
+                for (int w = 0; w < NW - 1; ++w) if (w < warp) cin = fma(aC[w], cin, aA[w]);
+                if (warp == NW - 1) sh->carry[pc][lane] = fma(C[R - 1], cin, A[R - 1]);
+            }
+        }
+
+        // ---- set-up of the tile being scanned ------------------------------------------
+        const StageT &S = stages[stage];
+        float vnext_f = 0.f;
+        bool first_prev_done = false;
+        if (P1) {
+            const int64_t ncol = (int64_t)nx_strip * W + lane;
+            const bool ncol_ok = ncol < p.B;
+            if (nx_k == 0) {
+                if (MODE == 0) nx_carry0 = (ACC)0;
+                else if (MODE == 1) nx_carry0 = ncol_ok ? (ACC)p.boot[ncol] : (ACC)0;
+                else nx_carry0 = ncol_ok ? (ACC)p.prev_ret[ncol] : (ACC)0;
+            }
+            if (MODE == 0 && warp == NW - 1 && nx_k == 0) vnext_f = ncol_ok ? p.boot[ncol] : 0.f;
+            if (MODE == 2 && warp == 0 && nx_k == 0) first_prev_done = ncol_ok ? (p.prev_done[ncol] != 0) : false;
+            mbar_wait(&sh->full[stage], phase);
+            if (MODE == 0) {
+                if (warp == NW - 1) { if (nx_k != 0) vnext_f = sh->halo[par ^ 1][lane]; }
+                else vnext_f = S.v[i0 + R][lane];
+            }
+        }
+        OutT &O = outs[pc];
+        // statistics of the tile being finalised: interior tiles without a mask accumulate inside the
+        // row loop (fills the issue slots the scan chain leaves free); others go through ystat[]
+        bool stats_fast = false;
+        int64_t s_col = 0;
+        bool s_col_ok = false;
+        if (P2 && HAS_STATS && !(p.debug & 1)) {
+            s_col = (int64_t)cu_strip * W + lane;
+            s_col_ok = s_col < p.B;
+            const bool strip_full = (int64_t)(cu_strip + 1) * W <= p.B;
+            stats_fast = p.valid == nullptr && strip_full && cu_t0 >= 0 && cu_t0 + TC <= T;
+            if (!st_has) {  // pivot: any value of the data's magnitude will do (uniform within the warp)
+                constexpr int u0 = REVERSE ? R - 1 : 0;
+                float y = to_f32(fma(C[u0], cin, A[u0]));
+                if (MODE == 1) y = __fsub_rn(y, vreg[u0]);
+                st_piv = __shfl_sync(0xffffffffu, y, 0);
+                st_has = true;
+            }
+        }
+        ACC a = (ACC)0, c = (ACC)1;
+        auto rows = [&](auto fast_tag) {
+            constexpr bool FAST = decltype(fast_tag)::value;
+            float ystat[(HAS_STATS && !FAST) ? R : 1];
+            (void)ystat;
+            float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
+#pragma unroll
+            for (int uu = 0; uu < R; ++uu) {
+                const int u = REVERSE ? R - 1 - uu : uu;
+                if (P2) {  // finalise row u of the previous tile from registers
+                    const float x = to_f32(fma(C[u], cin, A[u]));
+                    float y0;
+                    if (MODE == 0) {
+                        y0 = x;
+                        O.o[0][i0 + u][lane] = x;
+                        O.o[1][i0 + u][lane] = __fadd_rn(x, vreg[u]);
+                    } else if (MODE == 1) {
+                        y0 = __fsub_rn(x, vreg[u]);
+                        O.o[1][i0 + u][lane] = x;
+                        O.o[0][i0 + u][lane] = y0;
+                    } else {
+                        y0 = x;
+                        O.o[0][i0 + u][lane] = x;
+                    }
+                    if (HAS_PRE) O.o[PRE_SLOT][i0 + u][lane] = rpre[u];
+                    if (HAS_STATS) {
+                        if (FAST) {
+                            const float d = y0 - st_piv;
+                            if (uu & 1) { s1b += d; s2b = fmaf(d, d, s2b); }
+                            else { s1a += d; s2a = fmaf(d, d, s2a); }
+                        } else {
+                            ystat[u] = y0;
+                        }
+                    }
+                }
+                if (P1) {  // scan row u of the next tile
+                    float rf = S.r[i0 + u][lane];
+                    bool dn = S.d[i0 + u][lane] != 0;
+                    if (HAS_PRE) {
+                        rf = __double2float_rn((double)rf * inv_denom);
+                        rf = fminf(fmaxf(rf, clip_lo), clip_hi);
+                        rpre[u] = rf;
+                    }
+                    if (REVERSE) {
+                        const float vf = S.v[i0 + u][lane];
+                        vreg[u] = vf;
+                        const ACC cc = dn ? (ACC)0 : (MODE == 0 ? gl : gamma);
+                        if (MODE == 0) {
+                            const ACC delta = fma(gamma, (ACC)(dn ? 0.f : vnext_f), (ACC)rf) - (ACC)vf;
+                            a = fma(cc, a, delta);
+                            vnext_f = vf;
+                        } else {
+                            a = fma(cc, a, (ACC)rf);
+                        }
+                        c = cc * c;
+                    } else {
+                        if (uu == 0 && warp == 0 && nx_k == 0) dn = first_prev_done;
+                        const ACC cc = dn ? (ACC)0 : gamma;
+                        a = fma(cc, a, (ACC)rf);
+                        c = cc * c;
+                    }
+                    A[u] = a;
+                    C[u] = c;
+                }
+            }
+            if (P2 && HAS_STATS && !(p.debug & 1)) {
+                if (FAST) {
+                    st_n += R;
+                } else {
+                    const int u_lo = (int)((cu_t0 + i0 < 0) ? -(cu_t0 + i0) : 0);
+                    const int u_hi = (int)((T - (cu_t0 + i0) < R) ? (T - (cu_t0 + i0)) : R);
+                    const uint8_t *vp = (p.valid != nullptr) ? p.valid + (cu_t0 + i0) * p.ld_valid + s_col : nullptr;
+#pragma unroll
+                    for (int u = 0; u < R; ++u) {
+                        const float d = ystat[u] - st_piv;
+                        bool ok = s_col_ok && u >= u_lo && u < u_hi;
+                        if (ok && vp != nullptr) ok = vp[(int64_t)u * p.ld_valid] != 0;
+                        if (ok) {
+                            s1a += d;
+                            s2a = fmaf(d, d, s2a);
+                            ++st_n;
+                        }
+                    }
+                }
+                st_s1 += (double)(s1a + s1b);
+                st_s2 += (double)(s2a + s2b);
+            }
+        };
+        if constexpr (P2 && HAS_STATS) {
+            if (stats_fast) rows(std::true_type{});
+            else rows(std::false_type{});
+        } else {
+            rows(std::false_type{});
+        }
+        if (P1) {
+            sh->aggA[par][warp][lane] = a;
+            sh->aggC[par][warp][lane] = c;
+            if (MODE == 0 && warp == 0) sh->halo[par][lane] = vreg[0];
+        }
+        if (P2) fence_proxy_async_smem();  // staging-tile writes -> visible to the TMA store issued after the next barrier
+
+        // ---- advance the cursors ---------------------------------------------------------
+        if (P1) {
+            cu_strip = nx_strip; cu_k = nx_k; cu_carry0 = nx_carry0;
+            if (++nx_k == n_chunks) { nx_k = 0; nx_strip += gridDim.x; }
+            par ^= 1;
+            if (++stage == n_stages) { stage = 0; phase ^= 1u; }
+        }
+    };
+
+    if (n_tiles > 0) {
+        body(std::false_type{}, std::true_type{});
+        for (int j = 0; j + 1 < n_tiles; ++j) body(std::true_type{}, std::true_type{});
+        body(std::true_type{}, std::false_type{});
+    }
+
+    __syncthreads();
+    // after the last body: the final tile sits in outs[par ^ 1]
+    if (threadIdx.x == 0 && st_pending) store_tile(par ^ 1);
+    if (HAS_STATS && !(p.debug & 2)) {
+        Sums acc;
+        acc.n = (double)st_n; acc.s1 = st_s1; acc.s2 = st_s2; acc.piv = (double)st_piv;
+        moments_tail<true>(acc, p.tail, red_scratch);
+    }
     if (threadIdx.x == 0) tma_store_wait<0>();
 }
 
@@ -558,6 +878,12 @@ bool scan_chunked_supported(const float *reward, int64_t ld_r, const float *valu
     return tma_ok_u8(done, ld_d);
 }
 
+// tile geometry: 0 = auto, 1 = 8 warps x 8 rows (64-row tiles), 2 = 8 warps x 16 rows, 3 = 16 warps x 8 rows
+static int g_chunked_geom = 0;
+static int g_chunked_f32 = 0;        // 1: float32 affine maps (fast variant)
+static int g_scan_debug = 0;
+static int g_chunked_pipe = 1;       // 1: software-pipelined tile loop (default), 0: two-phase tile loop
+
 template <int MODE, typename ACC, int NW, int R, bool HAS_PRE, bool HAS_STATS>
 static int launch_chunked_inst(const chunked::TensorMaps &tm, chunked::Params p, int sms, cudaStream_t stream)
 {
@@ -567,13 +893,16 @@ static int launch_chunked_inst(const chunked::TensorMaps &tm, chunked::Params p,
     const size_t stage_bytes = sizeof(Stage<TC>);
     const size_t fixed_bytes = sizeof(Shared<ACC, NW>) + 2 * sizeof(OutTile<TC, N_OUT>);
     p.n_strips = (int)ceil_div(p.B, W);
+    p.debug = g_scan_debug;
     p.n_chunks = (int)ceil_div(p.T, TC);
     // few strips: one CTA per SM with a deep ring; many strips: several CTAs per SM, shallow rings.
     // 228 KB of shared memory per SM, 1 KB reserved per CTA, ~1 KB of static scratch per CTA.
     int ctas_per_sm = p.n_strips <= sms ? 1 : (p.n_strips <= 2 * sms ? 2 : 3);
     if (NW > 8) ctas_per_sm = 1;
-    auto kern = scan_chunked_kernel<MODE, ACC, NW, R, HAS_PRE, HAS_STATS>;
-    static thread_local size_t static_smem = ~(size_t)0;
+    auto kern = g_chunked_pipe ? scan_pipelined_kernel<MODE, ACC, NW, R, HAS_PRE, HAS_STATS>
+                               : scan_chunked_kernel<MODE, ACC, NW, R, HAS_PRE, HAS_STATS>;
+    static thread_local size_t static_smem_v[2] = {~(size_t)0, ~(size_t)0};
+    size_t &static_smem = static_smem_v[g_chunked_pipe ? 1 : 0];
     if (static_smem == ~(size_t)0) {
         cudaFuncAttributes attr;
         PLB_CUDA(cudaFuncGetAttributes(&attr, kern));
@@ -593,7 +922,8 @@ static int launch_chunked_inst(const chunked::TensorMaps &tm, chunked::Params p,
     p.n_stages = stages;
     const size_t smem = stage_bytes * stages + fixed_bytes;
     const int grid = p.n_strips < sms * ctas_per_sm ? p.n_strips : sms * ctas_per_sm;
-    static thread_local bool configured = false;
+    static thread_local bool configured_v[2] = {false, false};
+    bool &configured = configured_v[g_chunked_pipe ? 1 : 0];
     if (!configured) {
         PLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
         configured = true;
@@ -603,9 +933,6 @@ static int launch_chunked_inst(const chunked::TensorMaps &tm, chunked::Params p,
     return PLB_OK;
 }
 
-// tile geometry: 0 = auto, 1 = 8 warps x 8 rows (64-row tiles), 2 = 8 warps x 16 rows, 3 = 16 warps x 8 rows
-static int g_chunked_geom = 0;
-static int g_chunked_f32 = 0;        // 1: float32 affine maps (fast variant)
 
 struct ChunkedIO {
     const float *reward; int64_t ld_r;
@@ -795,6 +1122,8 @@ int plb_set_tuning(int key, int value)
     switch (key) {
         case 0: plb::g_chunked_geom = value; return PLB_OK;
         case 1: plb::g_chunked_f32 = value; return PLB_OK;
+        case 4: plb::g_chunked_pipe = value; return PLB_OK;
+        case 5: plb::g_scan_debug = value; return PLB_OK;
         case 3: plb::set_obs_variant(value); return PLB_OK;
         default: plb::set_error("unknown tuning key %d", key); return PLB_ERR_INVALID_ARGUMENT;
     }

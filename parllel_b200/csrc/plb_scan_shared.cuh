@@ -327,11 +327,13 @@ __device__ __forceinline__ void chan_update_scalar(double b_n, double b_mean, do
 // performs the only divisions of the whole reduction to write (count, mean, M2).
 // Must be called by ALL threads of EVERY CTA of the grid.  `scratch` >= 32 Sums.
 // ---------------------------------------------------------------------------------
+// WARP_PIVOT: `mine.piv` is uniform within every warp (the scans broadcast lane 0's first value).
+template <bool WARP_PIVOT = false>
 __device__ __forceinline__ void moments_tail(const Sums &mine, const MomentsTail &tail, Sums *scratch)
 {
     __shared__ bool is_last;
     __syncthreads();  // scratch may have been used before
-    const Sums blk = block_reduce_sums(mine, scratch);
+    const Sums blk = WARP_PIVOT ? block_reduce_sums_warp_pivot(mine, scratch) : block_reduce_sums(mine, scratch);
     if (tail.partials_only) {
         if (threadIdx.x == 0) {
             tail.partials[blockIdx.x] = blk;

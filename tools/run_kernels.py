@@ -61,12 +61,17 @@ def main():
     ap.add_argument("--rows", type=int, default=0)
     ap.add_argument("--f32", type=int, default=0)
     ap.add_argument("--obs-variant", type=int, default=0)
+    ap.add_argument("--debug", type=int, default=0)
+    ap.add_argument("--partials", type=int, default=1, help="gae_stats: publish per-CTA partials (as inside the fused step)")
+    ap.add_argument("--pipe", type=int, default=1, help="1: software-pipelined chunked scan, 0: two-phase")
     args = ap.parse_args()
     from parllel_b200 import _lib
     if args.rows:
         _lib.load().plb_set_tuning(0, args.rows)
     _lib.load().plb_set_tuning(1, args.f32)
     _lib.load().plb_set_tuning(3, args.obs_variant)
+    _lib.load().plb_set_tuning(4, args.pipe)
+    _lib.load().plb_set_tuning(5, args.debug)
     dev = torch.device("cuda:0")
     rng = np.random.default_rng(0)
     flush = torch.empty(256 * 2**20, dtype=torch.uint8, device=dev)  # > L2
@@ -93,7 +98,7 @@ def main():
                 lst = [EstimateAdvantage(0.99, args.lam), NormalizeAdvantage(tree)]
                 nbytes = 17 * T * B
             fz = FusedBatchTransforms(lst, use_cuda_graph=False)
-            ph = _lib.PHASE_B if args.what == "gae_stats" else _lib.PHASE_ALL
+            ph = (_lib.PHASE_B | (_lib.PHASE_PARTIALS if args.partials else 0)) if args.what == "gae_stats" else _lib.PHASE_ALL
             tf = lambda tr: fz(tr, phases=ph)
         elif args.what == "normadv":
             for tr in trees:
