@@ -480,7 +480,10 @@ int plb_normalize_observations_step_f32(float *obs, int64_t ld_obs, int64_t rows
         // kernels 85 us -> prefer the shared-memory slab, use the L2 variant when the slab is too tall
         int rc1 = PLB_ERR_UNSUPPORTED;
         const int variant = obs_variant();
-        if (variant != 2)
+        if (variant == 3)
+            rc1 = obs_step_cluster(obs, ld_obs, rows, cols, row_valid, mean, var, count, batch_count,
+                                   eps, flags, clip_lo, clip_hi, stream);
+        if (rc1 == PLB_ERR_UNSUPPORTED && variant != 2)
             rc1 = obs_step_single_pass(obs, ld_obs, rows, cols, row_valid, mean, var, count, batch_count,
                                        eps, flags, clip_lo, clip_hi, stream);
         if (rc1 == PLB_ERR_UNSUPPORTED && variant != 1)

@@ -366,10 +366,12 @@ def test_c2_shape_observation_step_vs_oracle():
     np.testing.assert_allclose(tf.obs_statistics.var, stats.var, rtol=5e-6)
 
 
-@pytest.mark.parametrize("variant", [1, 2])
-@pytest.mark.parametrize("B,F,masked", [(64, 192, False), (300, 52, True), (4100, 64, False), (17, 8, True)])
+@pytest.mark.parametrize("variant", [1, 2, 3])
+@pytest.mark.parametrize("B,F,masked", [(64, 192, False), (300, 52, True), (4100, 64, False), (17, 8, True),
+                                        (1024, 200, False), (256, 100, True), (1000, 64, False)])
 def test_observation_step_kernel_variants_vs_oracle(variant, B, F, masked):
-    """Both single-pass designs (shared-memory slab, two-pass L2 slab) and the fall-backs they defer to."""
+    """The single-pass designs (shared-memory slab, two-pass L2 slab, two-CTA cluster slab) and the
+    fall-backs they defer to (the cluster slab needs an even B >= 128 and F >= 64)."""
     from parllel_b200 import _lib
     from parllel_b200.transforms import NormalizeObservations
     rng = np.random.default_rng(B + F)
@@ -416,7 +418,7 @@ def test_observation_clip_extension():
     for t in range(2):
         O.normalize_observations_step(ref[t], stats)
     ref = np.clip(ref, -1.5, 1.5)
-    for variant in (0, 1, 2):
+    for variant in (0, 1, 2, 3):
         _lib.load().plb_set_tuning(3, variant)
         d = torch.from_numpy(obs).cuda()
         NormalizeObservations({"observation": d}, obs_shape=(40,), initial_count=10, clip=1.5).normalize_batch(d)
