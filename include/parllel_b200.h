@@ -133,6 +133,18 @@ PLB_API int plb_batch_moments_f32(
     double *moments_out,
     void *workspace, size_t workspace_bytes, plb_stream_t stream);
 
+/* Moments of the float32 difference x - sub over the same region: the residual term of
+ * explained_variance (parllel/torch/utils.py:135-156: 1 - Var[y_true - y_pred] / Var[y_true]). */
+PLB_API int plb_residual_moments_f32(const float *x, int64_t ld_x, const float *sub, int64_t ld_sub,
+                                     int64_t rows, int64_t cols, const uint8_t *valid, int64_t ld_valid,
+                                     double *moments_out, void *workspace, size_t workspace_bytes,
+                                     plb_stream_t stream);
+
+/* Valid mask of a recurrent batch (parllel/samplers/recurrent.py:102-103,141-142):
+ * valid[0] = 1; valid[t+1] = valid[t] & ~done[t], for t + 1 < T.  1-byte masks, row strides in elements. */
+PLB_API int plb_valid_prefix_u8(const uint8_t *done, int64_t ld_done, int64_t T, int64_t B,
+                                uint8_t *valid_out, int64_t ld_valid, plb_stream_t stream);
+
 /* Per-column moments of a [rows, cols] region over the rows with row_valid != 0
  * (row_valid may be NULL).  Writes count_out[1], mean_out[cols], m2_out[cols]. */
 PLB_API size_t plb_column_moments_workspace_bytes(int64_t rows, int64_t cols);

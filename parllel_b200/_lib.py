@@ -73,6 +73,10 @@ _SIGNATURES = {
     "plb_batch_moments_workspace_bytes": ([], c_size_t),
     "plb_batch_moments_f32": (
         [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_size_t, c_void_p], c_int),
+    "plb_residual_moments_f32": (
+        [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_size_t,
+         c_void_p], c_int),
+    "plb_valid_prefix_u8": ([c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p], c_int),
     "plb_column_moments_workspace_bytes": ([c_int64, c_int64], c_size_t),
     "plb_column_moments_f32": (
         [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,

@@ -9,10 +9,12 @@ namespace plb {
 // ---------------------------------------------------------------------------------
 // scalar moments over a [rows, cols] region (optionally masked per element)
 // ---------------------------------------------------------------------------------
-template <bool VEC4, bool MASKED>
+// HAS_SUB: moments of the float32 difference x - sub (explained_variance's residual)
+template <bool VEC4, bool MASKED, bool HAS_SUB = false>
 __global__ void __launch_bounds__(256)
 batch_moments_kernel(const float *__restrict__ x, int64_t ld_x, int64_t rows, int64_t cols,
-                     const uint8_t *__restrict__ valid, int64_t ld_v, MomentsTail tail)
+                     const uint8_t *__restrict__ valid, int64_t ld_v, MomentsTail tail,
+                     const float *__restrict__ sub = nullptr, int64_t ld_s = 0)
 {
     __shared__ Sums scratch[32];
     PivotAcc acc;
@@ -33,6 +35,11 @@ batch_moments_kernel(const float *__restrict__ x, int64_t ld_x, int64_t rows, in
                     const int64_t r = (rows == 1) ? 0 : i / vpr;
                     const int64_t c = (i - r * vpr) << 2;
                     v[u] = *reinterpret_cast<const float4 *>(x + r * ld_x + c);
+                    if (HAS_SUB) {
+                        const float4 q = *reinterpret_cast<const float4 *>(sub + r * ld_s + c);
+                        v[u].x = __fsub_rn(v[u].x, q.x); v[u].y = __fsub_rn(v[u].y, q.y);
+                        v[u].z = __fsub_rn(v[u].z, q.z); v[u].w = __fsub_rn(v[u].w, q.w);
+                    }
                     if (MASKED) m[u] = *reinterpret_cast<const uchar4 *>(valid + r * ld_v + c);
                 }
             }
@@ -52,7 +59,8 @@ batch_moments_kernel(const float *__restrict__ x, int64_t ld_x, int64_t rows, in
         for (int64_t i = tid; i < total; i += nthreads) {
             const int64_t r = (rows == 1) ? 0 : i / cols;
             const int64_t c = i - r * cols;
-            if (!MASKED || valid[r * ld_v + c]) acc.add(x[r * ld_x + c]);
+            if (!MASKED || valid[r * ld_v + c])
+                acc.add(HAS_SUB ? __fsub_rn(x[r * ld_x + c], sub[r * ld_s + c]) : x[r * ld_x + c]);
         }
     }
     moments_tail(acc.sums(), tail, scratch);
@@ -117,6 +125,32 @@ column_moments_finalize_kernel(const Moments *__restrict__ partials, int64_t col
     mean_out[c] = acc.mean;
     m2_out[c] = acc.m2;
     if (c == 0) count_out[0] = acc.n;
+}
+
+// ---------------------------------------------------------------------------------
+// valid mask of a recurrent batch (parllel/samplers/recurrent.py:102-103,141-142):
+//   valid[0] = True; valid[t+1] = valid[t] & ~done[t]     (one thread per environment column)
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+valid_prefix_kernel(const uint8_t *__restrict__ done, int64_t ld_d, int64_t T, int64_t B,
+                    uint8_t *__restrict__ valid, int64_t ld_v)
+{
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    uint8_t ok = 1;
+    constexpr int U = 8;
+    for (int64_t t0 = 0; t0 < T; t0 += U) {
+        uint8_t d[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) d[u] = (t0 + u < T) ? done[(t0 + u) * ld_d + b] : (uint8_t)0;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (t0 + u < T) {
+                valid[(t0 + u) * ld_v + b] = ok;
+                ok = (ok && !d[u]) ? 1 : 0;
+            }
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------
@@ -246,29 +280,31 @@ extern "C" {
 
 size_t plb_batch_moments_workspace_bytes(void) { return plb::MOMENTS_WS_BYTES; }
 
-int plb_batch_moments_f32(const float *x, int64_t ld_x, int64_t rows, int64_t cols,
-                          const uint8_t *valid, int64_t ld_valid, double *moments_out,
-                          void *workspace, size_t workspace_bytes, plb_stream_t stream_)
+static int batch_moments_impl(const float *x, int64_t ld_x, const float *sub, int64_t ld_sub, int64_t rows, int64_t cols,
+                              const uint8_t *valid, int64_t ld_valid, double *moments_out,
+                              void *workspace, size_t workspace_bytes, cudaStream_t stream)
 {
     using namespace plb;
-    cudaStream_t stream = (cudaStream_t)stream_;
     PLB_REQUIRE(rows >= 0 && cols >= 0, PLB_ERR_INVALID_ARGUMENT, "negative extent");
     PLB_REQUIRE(moments_out != nullptr, PLB_ERR_INVALID_ARGUMENT, "null output");
     PLB_REQUIRE(rows * cols == 0 || x != nullptr, PLB_ERR_INVALID_ARGUMENT, "null input");
     PLB_REQUIRE(workspace != nullptr && workspace_bytes >= MOMENTS_WS_BYTES, PLB_ERR_WORKSPACE,
                 "batch moments need %zu workspace bytes, got %zu", MOMENTS_WS_BYTES, workspace_bytes);
-    PLB_REQUIRE(rows * cols == 0 || (ld_x >= cols && (valid == nullptr || ld_valid >= cols)),
+    PLB_REQUIRE(rows * cols == 0 || (ld_x >= cols && (valid == nullptr || ld_valid >= cols) &&
+                                     (sub == nullptr || ld_sub >= cols)),
                 PLB_ERR_INVALID_ARGUMENT, "row stride smaller than row length");
     // flatten dense regions so the kernel skips the row/column split
-    if (ld_x == cols && (valid == nullptr || ld_valid == cols)) {
+    if (ld_x == cols && (valid == nullptr || ld_valid == cols) && (sub == nullptr || ld_sub == cols)) {
         cols = rows * cols;
         rows = cols > 0 ? 1 : 0;
         ld_x = cols;
         ld_valid = cols;
+        ld_sub = cols;
     }
     const int64_t total = rows * cols;
     const bool vec = (cols % 4 == 0) && (ld_x % 4 == 0) && aligned(x, 16) &&
-                     (valid == nullptr || ((ld_valid % 4 == 0) && aligned(valid, 4)));
+                     (valid == nullptr || ((ld_valid % 4 == 0) && aligned(valid, 4))) &&
+                     (sub == nullptr || ((ld_sub % 4 == 0) && aligned(sub, 16)));
     const int sms = sm_count();
     PLB_REQUIRE(sms > 0, PLB_ERR_UNSUPPORTED, "no CUDA device");
     int64_t blocks = ceil_div(vec ? ceil_div(total, 4) : total, 256 * 4);
@@ -276,13 +312,46 @@ int plb_batch_moments_f32(const float *x, int64_t ld_x, int64_t rows, int64_t co
     if (blocks > (int64_t)sms * 8) blocks = (int64_t)sms * 8;
     if (blocks > MOMENTS_MAX_PARTIALS) blocks = MOMENTS_MAX_PARTIALS;
     const MomentsTail tail = make_tail(moments_out, workspace);
-    if (vec) {
-        if (valid) batch_moments_kernel<true, true><<<(unsigned)blocks, 256, 0, stream>>>(x, ld_x, rows, cols, valid, ld_valid, tail);
-        else batch_moments_kernel<true, false><<<(unsigned)blocks, 256, 0, stream>>>(x, ld_x, rows, cols, valid, ld_valid, tail);
+#define PLB_BM_LAUNCH(V, M, S) \
+    batch_moments_kernel<V, M, S><<<(unsigned)blocks, 256, 0, stream>>>(x, ld_x, rows, cols, valid, ld_valid, tail, sub, ld_sub)
+    if (sub != nullptr) {
+        if (vec) { if (valid) PLB_BM_LAUNCH(true, true, true); else PLB_BM_LAUNCH(true, false, true); }
+        else { if (valid) PLB_BM_LAUNCH(false, true, true); else PLB_BM_LAUNCH(false, false, true); }
     } else {
-        if (valid) batch_moments_kernel<false, true><<<(unsigned)blocks, 256, 0, stream>>>(x, ld_x, rows, cols, valid, ld_valid, tail);
-        else batch_moments_kernel<false, false><<<(unsigned)blocks, 256, 0, stream>>>(x, ld_x, rows, cols, valid, ld_valid, tail);
+        if (vec) { if (valid) PLB_BM_LAUNCH(true, true, false); else PLB_BM_LAUNCH(true, false, false); }
+        else { if (valid) PLB_BM_LAUNCH(false, true, false); else PLB_BM_LAUNCH(false, false, false); }
     }
+#undef PLB_BM_LAUNCH
+    PLB_LAUNCH_CHECK();
+    return PLB_OK;
+}
+
+int plb_batch_moments_f32(const float *x, int64_t ld_x, int64_t rows, int64_t cols,
+                          const uint8_t *valid, int64_t ld_valid, double *moments_out,
+                          void *workspace, size_t workspace_bytes, plb_stream_t stream_)
+{
+    return batch_moments_impl(x, ld_x, nullptr, 0, rows, cols, valid, ld_valid, moments_out, workspace, workspace_bytes,
+                              (cudaStream_t)stream_);
+}
+
+int plb_residual_moments_f32(const float *x, int64_t ld_x, const float *sub, int64_t ld_sub, int64_t rows, int64_t cols,
+                             const uint8_t *valid, int64_t ld_valid, double *moments_out,
+                             void *workspace, size_t workspace_bytes, plb_stream_t stream_)
+{
+    PLB_REQUIRE(rows * cols == 0 || sub != nullptr, PLB_ERR_INVALID_ARGUMENT, "null subtrahend");
+    return batch_moments_impl(x, ld_x, sub, ld_sub, rows, cols, valid, ld_valid, moments_out, workspace, workspace_bytes,
+                              (cudaStream_t)stream_);
+}
+
+int plb_valid_prefix_u8(const uint8_t *done, int64_t ld_done, int64_t T, int64_t B, uint8_t *valid_out, int64_t ld_valid,
+                        plb_stream_t stream_)
+{
+    using namespace plb;
+    PLB_REQUIRE(T >= 0 && B >= 0, PLB_ERR_INVALID_ARGUMENT, "negative extent");
+    if (T == 0 || B == 0) return PLB_OK;
+    PLB_REQUIRE(done != nullptr && valid_out != nullptr, PLB_ERR_INVALID_ARGUMENT, "null pointer");
+    PLB_REQUIRE(ld_done >= B && ld_valid >= B, PLB_ERR_INVALID_ARGUMENT, "row stride smaller than row length");
+    valid_prefix_kernel<<<(unsigned)ceil_div(B, 256), 256, 0, (cudaStream_t)stream_>>>(done, ld_done, T, B, valid_out, ld_valid);
     PLB_LAUNCH_CHECK();
     return PLB_OK;
 }

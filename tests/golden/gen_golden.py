@@ -279,6 +279,43 @@ def gen_dataloader():
     save("dataloader", **out)
 
 
+def gen_metrics():
+    """explained_variance (torch/utils.py:135-156), RunningMeanStdModel (torch/models.py:193-230, single
+    process) and the recurrent sampler's valid recursion (samplers/recurrent.py:102-103,141-142)."""
+    import torch
+    from parllel.torch.models import RunningMeanStdModel
+    from parllel.torch.utils import explained_variance
+
+    rng = np.random.default_rng(21)
+    out = {}
+    for i, (n, noise) in enumerate([(5000, 0.3), (1237, 2.0), (64, 0.0)]):
+        y_true = (2.0 + 1.5 * rng.standard_normal(n)).astype(np.float32)
+        y_pred = (y_true + noise * rng.standard_normal(n)).astype(np.float32)
+        out[f"ev{i}_true"], out[f"ev{i}_pred"] = y_true, y_pred
+        out[f"ev{i}"] = np.float64(explained_variance(torch.from_numpy(y_pred), torch.from_numpy(y_true)))
+    const = np.full(100, 3.0, np.float32)
+    out["ev_const"] = np.float64(explained_variance(torch.from_numpy(const * 0.5), torch.from_numpy(const)))
+
+    model = RunningMeanStdModel((5, 3))
+    xs = (4.0 + 2.0 * rng.standard_normal((3, 6, 10, 5, 3))).astype(np.float32)
+    for k in range(3):
+        model.update(torch.from_numpy(xs[k]))
+        out[f"rms{k}_mean"], out[f"rms{k}_var"] = model.mean.numpy().copy(), model.var.numpy().copy()
+        out[f"rms{k}_count"] = model.count.numpy().copy()
+    out["rms_x"] = xs
+
+    # the sampler's statement, step by step, on a [T + 1, B] valid array (the last row is the padding row)
+    T, B = 37, 29
+    done = rng.random((T, B)) < 0.07
+    valid = np.zeros((T + 1, B), np.bool_)
+    valid[0] = True
+    valid[1:] = False
+    for t in range(T):
+        valid[t + 1] = np.logical_and(valid[t], np.logical_not(done[t]))
+    out["valid_done"], out["valid_mask"] = done, valid[:T]
+    save("metrics", **out)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1:  # regenerate selected fixtures only: python gen_golden.py multi_advantage
         for name in sys.argv[1:]:
@@ -297,3 +334,4 @@ if __name__ == "__main__":
     gen_multi_advantage()
     gen_replay()
     gen_dataloader()
+    gen_metrics()

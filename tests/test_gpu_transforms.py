@@ -516,3 +516,36 @@ def test_zero_extent_calls_are_noops():
     # moments of an empty region: count 0 (mean/M2 0), workspace left reusable
     _lib.check(lib.plb_batch_moments_f32(0, 0, 0, 0, 0, 0, out.data_ptr(), ws.data_ptr(), ws.numel(), s))
     assert out.cpu().tolist() == [0.0, 0.0, 0.0]
+
+
+def test_metrics_vs_reference_golden(golden):
+    """explained_variance / RunningMeanStdModel / valid_mask on the device against the reference's outputs."""
+    from parllel_b200.metrics import explained_variance, valid_mask
+    from parllel_b200.models import RunningMeanStdModel
+    g = golden("metrics")
+    for i in range(3):
+        ev = explained_variance(torch.from_numpy(g[f"ev{i}_pred"]).cuda(), torch.from_numpy(g[f"ev{i}_true"]).cuda())
+        ref = float(g[f"ev{i}"])
+        assert abs(ev - ref) <= 2e-6 * max(1.0, abs(ref)), (i, ev, ref)
+        assert abs(ev - O.explained_variance(g[f"ev{i}_pred"], g[f"ev{i}_true"])) <= 1e-9
+    const = torch.full((100,), 3.0, device="cuda")
+    assert np.isnan(explained_variance(const * 0.5, const))
+    model = RunningMeanStdModel((5, 3))
+    for k in range(3):
+        model.update(torch.from_numpy(g["rms_x"][k]).cuda())
+        np.testing.assert_allclose(model.mean.cpu().numpy(), g[f"rms{k}_mean"], rtol=2e-6)
+        np.testing.assert_allclose(model.var.cpu().numpy(), g[f"rms{k}_var"], rtol=1e-5)
+        assert float(model.count) == float(g[f"rms{k}_count"])
+    got = valid_mask(torch.from_numpy(g["valid_done"]).cuda())
+    np.testing.assert_array_equal(got.cpu().numpy(), g["valid_mask"])
+
+
+@pytest.mark.parametrize("T,B", [(1, 1), (9, 300), (130, 4097)])
+def test_valid_mask_vs_oracle(T, B):
+    from parllel_b200.metrics import valid_mask
+    rng = np.random.default_rng(T + B)
+    done = rng.random((T, B)) < 0.05
+    base = torch.zeros((T, B + 3), dtype=torch.bool, device="cuda")  # strided output
+    out = valid_mask(torch.from_numpy(done).cuda(), out=base[:, :B])
+    np.testing.assert_array_equal(out.cpu().numpy(), O.valid_prefix(done))
+    assert not bool(base[:, B:].any())
