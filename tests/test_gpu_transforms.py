@@ -549,3 +549,47 @@ def test_valid_mask_vs_oracle(T, B):
     out = valid_mask(torch.from_numpy(done).cuda(), out=base[:, :B])
     np.testing.assert_array_equal(out.cpu().numpy(), O.valid_prefix(done))
     assert not bool(base[:, B:].any())
+
+
+def test_c2_full_size_observation_step_properties():
+    """BASELINE config C2 step shape (B=1024, F=3*84*84): two dependent steps; the running statistics and
+    the normalised output against a float64 restatement of norm_obs.py:57-76 evaluated with torch on the
+    same device (an independent checker at a size the CPU oracle would take minutes for), and the three
+    single-pass kernel designs against each other."""
+    from parllel_b200 import _lib
+    from parllel_b200.transforms import NormalizeObservations
+    B, shape = 1024, (3, 84, 84)
+    F = int(np.prod(shape))
+    g = torch.Generator(device="cuda").manual_seed(5)
+    obs = 5.0 + 3.0 * torch.randn((2, B) + shape, device="cuda", generator=g)
+    mean = torch.zeros(F, dtype=torch.float64, device="cuda")
+    var = torch.ones(F, dtype=torch.float64, device="cuda")
+    count = 10000.0
+    expect = []
+    for t in range(2):
+        x = obs[t].reshape(B, F).to(torch.float64)
+        bm, bv = x.mean(0), x.var(0, unbiased=False)
+        delta, total = bm - mean, count + B
+        mean = mean + delta * B / total
+        var = (var * count + bv * B + delta ** 2 * count * B / total) / total
+        count = total
+        expect.append(((x - mean) / torch.sqrt(var + 1e-6)).to(torch.float32))
+    results = {}
+    for variant in (1, 2, 3):
+        _lib.load().plb_set_tuning(3, variant)
+        try:
+            d = obs.clone()
+            tf = NormalizeObservations({"observation": d}, obs_shape=shape, initial_count=10000)
+            for t in range(2):
+                tf._step(d[t], None, d.device)
+        finally:
+            _lib.load().plb_set_tuning(3, 0)
+        np.testing.assert_allclose(tf.obs_statistics.mean.reshape(-1), mean.cpu().numpy(), rtol=1e-6, atol=1e-7)
+        np.testing.assert_allclose(tf.obs_statistics.var.reshape(-1), var.cpu().numpy(), rtol=2e-6)
+        assert float(tf.obs_statistics.count) == count
+        for t in range(2):
+            err = (d[t].reshape(B, F) - expect[t]).abs().max().item()
+            assert err <= 1e-5, (variant, t, err)
+        results[variant] = d
+    assert (results[1] - results[2]).abs().max().item() <= 2e-6
+    assert (results[1] - results[3]).abs().max().item() <= 2e-6
