@@ -2,7 +2,13 @@
 //   stats.update(obs[valid]); obs[:] = (obs - stats.mean) / sqrt(stats.var + eps)
 // for one [B, F] float32 step with per-feature running statistics (float64).
 //
-// Each CTA owns a [B rows x 16 columns] slab: TMA brings the whole slab into shared memory once,
+// Four designs live here; plb_norm.cu picks (default: variant D, then A, then B, then three kernels):
+//   A  obs::obs_step_kernel            shared-memory slab, TMA in / TMA out
+//   B  obs_l2::obs_step_l2_kernel      two passes over a 256-byte-wide slab, second one served by L2
+//   C  obs_cl::obs_step_cluster_kernel 32-column slab split by rows over a two-CTA cluster (DSMEM)
+//   D  obs_lsu::obs_step_lsu_kernel    shared-memory slab, cp.async in / 128-bit global stores out
+//
+// Variant A.  Each CTA owns a [B rows x 16 columns] slab: TMA brings the whole slab into shared memory once,
 // the per-column batch moments are reduced from shared memory (pivot-shifted float64 sums,
 // division-free tree), merged into the running state with the reference's Chan update
 // (running_mean_std.py:23-30), the slab is normalised in place in shared memory and leaves by TMA
@@ -623,7 +629,240 @@ int obs_step_cluster(float *x, int64_t ld, int64_t rows, int64_t cols, const uin
     return PLB_OK;
 }
 
-static int g_obs_variant = 0;  // 0 auto, 1 shared-memory slab (TMA), 2 two-pass L2 slab, 3 two-CTA cluster slab
+// ---------------------------------------------------------------------------------------------
+// Variant D: the shared-memory slab of variant A filled and drained by the load/store units instead
+// of the TMA: cp.async (16 bytes per thread) in, 128-bit global stores straight from registers out.
+// Same [rows x 16 columns] slab and three CTAs per SM; the pivot of every column is its row-0 value,
+// so all partial sums of a column share it and merge by plain addition.
+// ---------------------------------------------------------------------------------------------
+namespace obs_lsu {
+
+constexpr int THREADS = 256;
+constexpr int NWARPS = THREADS / 32;
+
+struct Params {
+    float *x; int64_t ld;
+    int64_t rows, cols;
+    const uint8_t *row_valid;
+    double *mean, *var;
+    const double *count;
+    double *batch_count_out;
+    double eps;
+    float clip_lo, clip_hi;
+    int flags;
+    int n_slabs;
+};
+
+// FC columns per slab; thread (g, l) takes the float4 lane l of rows g, g+GROUPS, ...
+template <int FC>
+__global__ void __launch_bounds__(THREADS)
+obs_step_lsu_kernel(const Params p)
+{
+    constexpr int LANES = FC / 4;
+    constexpr int GROUPS = THREADS / LANES;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float4 (*slab)[LANES] = reinterpret_cast<float4 (*)[LANES]>(smem_raw);  // [rows][4 x float4]
+    __shared__ double w_s1[NWARPS][FC], w_s2[NWARPS][FC];
+    __shared__ unsigned w_n[NWARPS];
+    __shared__ float4 s_mu_hi[LANES], s_mu_lo[LANES], s_inv_hi[LANES], s_inv_lo[LANES];
+
+    const int l = threadIdx.x % LANES, g = threadIdx.x / LANES;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nrows = (int)p.rows;
+    const double cnt = p.count[0];
+    if ((int)blockIdx.x < p.n_slabs && (int64_t)blockIdx.x * FC + 4 * l < p.cols) {
+        const float *first = p.x + (int64_t)blockIdx.x * FC + 4 * l;
+        for (int r = g; r < nrows; r += GROUPS) {  // all requests of the first slab in flight at once
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&slab[r][l]);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(first + (int64_t)r * p.ld) : "memory");
+        }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    for (int s = blockIdx.x; s < p.n_slabs; s += gridDim.x) {
+        const int64_t c0 = (int64_t)s * FC + 4 * l;
+        const bool col_ok = c0 < p.cols;  // cols % 4 == 0: a float4 is entirely in or out
+        float *base = p.x + c0;
+        // ---- the slab was requested by this thread itself (before the loop, or while it drained the
+        // previous slab): wait for the own requests, then for everybody's
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+
+        // ---- per-column moments around the row-0 pivot -----------------------------------------
+        const float4 piv = col_ok ? slab[0][l] : make_float4(0.f, 0.f, 0.f, 0.f);
+        double S1[4] = {0.0, 0.0, 0.0, 0.0}, S2[4] = {0.0, 0.0, 0.0, 0.0};
+        unsigned n_acc = 0;
+        if (col_ok) {
+            constexpr int RUN = 16;
+            for (int r0 = g; r0 < nrows; r0 += GROUPS * RUN) {
+                float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+                for (int k = 0; k < RUN; ++k) {
+                    const int r = r0 + k * GROUPS;
+                    if (r < nrows && (p.row_valid == nullptr || p.row_valid[r] != 0)) {
+                        const float4 v = slab[r][l];
+                        const float d0 = v.x - piv.x, d1 = v.y - piv.y, d2 = v.z - piv.z, d3 = v.w - piv.w;
+                        s1[0] += d0; s2[0] = fmaf(d0, d0, s2[0]);
+                        s1[1] += d1; s2[1] = fmaf(d1, d1, s2[1]);
+                        s1[2] += d2; s2[2] = fmaf(d2, d2, s2[2]);
+                        s1[3] += d3; s2[3] = fmaf(d3, d3, s2[3]);
+                        ++n_acc;
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { S1[q] += (double)s1[q]; S2[q] += (double)s2[q]; }
+            }
+        }
+        // the 8 row groups of a warp share their columns' pivots: plain shuffle adds
+#pragma unroll
+        for (int d = LANES; d < 32; d <<= 1) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                S1[q] += __shfl_xor_sync(0xffffffffu, S1[q], d);
+                S2[q] += __shfl_xor_sync(0xffffffffu, S2[q], d);
+            }
+            n_acc += __shfl_xor_sync(0xffffffffu, n_acc, d);
+        }
+        if (lane < LANES) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { w_s1[warp][4 * lane + q] = S1[q]; w_s2[warp][4 * lane + q] = S2[q]; }
+            if (lane == 0) w_n[warp] = n_acc;
+        }
+        __syncthreads();
+        if (threadIdx.x < FC) {
+            const int c = threadIdx.x;
+            const int64_t col = (int64_t)s * FC + c;
+            Sums tot;
+            tot.n = 0.0; tot.s1 = 0.0; tot.s2 = 0.0;
+            tot.piv = (double)reinterpret_cast<const float *>(&slab[0][0])[c];
+            for (int w = 0; w < NWARPS; ++w) { tot.n += (double)w_n[w]; tot.s1 += w_s1[w][c]; tot.s2 += w_s2[w][c]; }
+            double mean = 0.0, var = 1.0;
+            if (col < p.cols) {
+                const Moments m = to_moments(tot);
+                mean = p.mean[col];
+                var = p.var[col];
+                chan_update_scalar(m.n, m.mean, m.m2, cnt, p.flags, mean, var);
+                p.mean[col] = mean;
+                p.var[col] = var;
+                if (s == 0 && c == 0) p.batch_count_out[0] = m.n;
+            }
+            const double inv = 1.0 / sqrt(__dadd_rn(var, p.eps));
+            const float mh = __double2float_rn(mean), ih = __double2float_rn(inv);
+            reinterpret_cast<float *>(s_mu_hi)[c] = mh;
+            reinterpret_cast<float *>(s_mu_lo)[c] = __double2float_rn(mean - (double)mh);
+            reinterpret_cast<float *>(s_inv_hi)[c] = ih;
+            reinterpret_cast<float *>(s_inv_lo)[c] = __double2float_rn(inv - (double)ih);
+        }
+        __syncthreads();
+
+        // ---- normalise from shared memory, store straight to global; every slab element is owned by
+        // one thread in all three phases, so as soon as a thread has drained a batch of its rows it
+        // requests the same rows of the CTA's next slab into the same places: the next load overlaps
+        // this slab's store phase
+        const int s_next = s + (int)gridDim.x;
+        const bool next_ok = s_next < p.n_slabs && (int64_t)s_next * FC + 4 * l < p.cols;
+        const float *next_base = p.x + (int64_t)s_next * FC + 4 * l;
+        {
+            float4 mh, ml, ih, il;
+            if (col_ok) { mh = s_mu_hi[l]; ml = s_mu_lo[l]; ih = s_inv_hi[l]; il = s_inv_lo[l]; }
+            constexpr int U = 4;
+            for (int r0 = g; r0 < nrows; r0 += GROUPS * U) {
+                if (col_ok) {
+                    float4 v[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const int r = r0 + u * GROUPS;
+                        if (r < nrows) v[u] = slab[r][l];
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const int r = r0 + u * GROUPS;
+                        if (r < nrows) {
+                            float4 o;
+                            float d;
+                            d = (v[u].x - mh.x) - ml.x; o.x = fminf(fmaxf(fmaf(d, ih.x, d * il.x), p.clip_lo), p.clip_hi);
+                            d = (v[u].y - mh.y) - ml.y; o.y = fminf(fmaxf(fmaf(d, ih.y, d * il.y), p.clip_lo), p.clip_hi);
+                            d = (v[u].z - mh.z) - ml.z; o.z = fminf(fmaxf(fmaf(d, ih.z, d * il.z), p.clip_lo), p.clip_hi);
+                            d = (v[u].w - mh.w) - ml.w; o.w = fminf(fmaxf(fmaf(d, ih.w, d * il.w), p.clip_lo), p.clip_hi);
+                            *reinterpret_cast<float4 *>(base + (int64_t)r * p.ld) = o;
+                        }
+                    }
+                }
+                if (next_ok) {
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const int r = r0 + u * GROUPS;
+                        if (r < nrows) {
+                            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&slab[r][l]);
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(next_base + (int64_t)r * p.ld) : "memory");
+                        }
+                    }
+                }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+        // no barrier here: the next iteration's first barrier orders this slab's shared-memory reads
+        // (column constants, warp sums) before their next writes; slab elements are thread-private
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
+}  // namespace obs_lsu
+
+static int g_obs_lsu_cols = 16;  // slab width of variant D (plb_set_tuning key 7: 8, 16 or 32)
+void set_obs_lsu_cols(int v) { g_obs_lsu_cols = v; }
+
+template <int FC>
+static int obs_step_lsu_inst(const obs_lsu::Params &p0, cudaStream_t stream)
+{
+    using namespace obs_lsu;
+    Params p = p0;
+    const size_t slab_bytes = (size_t)p.rows * FC * sizeof(float);
+    static thread_local size_t static_bytes = 0;
+    if (static_bytes == 0) {
+        cudaFuncAttributes attr;
+        PLB_CUDA(cudaFuncGetAttributes(&attr, obs_step_lsu_kernel<FC>));
+        static_bytes = attr.sharedSizeBytes;
+    }
+    const size_t avail = 227 * 1024 - static_bytes;
+    if (slab_bytes > avail) return PLB_ERR_UNSUPPORTED;
+    const int sms = sm_count();
+    PLB_REQUIRE(sms > 0, PLB_ERR_UNSUPPORTED, "no CUDA device");
+    p.n_slabs = (int)ceil_div(p.cols, FC);
+    int ctas_per_sm = (int)((228 * 1024) / (slab_bytes + static_bytes + 1024));
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+    if (ctas_per_sm > 8) ctas_per_sm = 8;
+    const int grid = p.n_slabs < sms * ctas_per_sm ? p.n_slabs : sms * ctas_per_sm;
+    static thread_local bool configured = false;
+    if (!configured) {
+        PLB_CUDA(cudaFuncSetAttribute(obs_step_lsu_kernel<FC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)avail));
+        configured = true;
+    }
+    obs_step_lsu_kernel<FC><<<grid, THREADS, slab_bytes, stream>>>(p);
+    PLB_LAUNCH_CHECK();
+    return PLB_OK;
+}
+
+int obs_step_lsu(float *x, int64_t ld, int64_t rows, int64_t cols, const uint8_t *row_valid,
+                 double *mean, double *var, const double *count, double *batch_count_out,
+                 double eps, int flags, float clip_lo, float clip_hi, cudaStream_t stream)
+{
+    using namespace obs_lsu;
+    if (!(aligned(x, 16) && ld % 4 == 0 && cols % 4 == 0) || rows < 1 || rows > (int64_t)INT32_MAX / 2 ||
+        cols > (int64_t)INT32_MAX / 2)
+        return PLB_ERR_UNSUPPORTED;
+    Params p = {};
+    p.x = x; p.ld = ld; p.rows = rows; p.cols = cols;
+    p.row_valid = row_valid;
+    p.mean = mean; p.var = var; p.count = count;
+    p.batch_count_out = batch_count_out;
+    p.eps = eps; p.flags = flags;
+    p.clip_lo = clip_lo; p.clip_hi = clip_hi;
+    if (g_obs_lsu_cols == 8) return obs_step_lsu_inst<8>(p, stream);
+    if (g_obs_lsu_cols == 32) return obs_step_lsu_inst<32>(p, stream);
+    return obs_step_lsu_inst<16>(p, stream);
+}
+
+static int g_obs_variant = 0;  // 0 auto, 1 shared-memory slab (TMA), 2 two-pass L2 slab, 3 two-CTA cluster slab, 4 load/store-unit slab
 int obs_variant() { return g_obs_variant; }
 void set_obs_variant(int v) { g_obs_variant = v; }
 

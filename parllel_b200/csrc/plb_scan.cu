@@ -1129,6 +1129,7 @@ int plb_set_tuning(int key, int value)
         case 1: plb::g_chunked_f32 = value; return PLB_OK;
         case 4: plb::g_chunked_pipe = value; return PLB_OK;
         case 5: plb::g_scan_debug = value; return PLB_OK;
+        case 7: plb::set_obs_lsu_cols(value); return PLB_OK;
         case 3: plb::set_obs_variant(value); return PLB_OK;
         default: plb::set_error("unknown tuning key %d", key); return PLB_ERR_INVALID_ARGUMENT;
     }

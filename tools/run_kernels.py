@@ -62,6 +62,7 @@ def main():
     ap.add_argument("--f32", type=int, default=0)
     ap.add_argument("--obs-variant", type=int, default=0)
     ap.add_argument("--debug", type=int, default=0)
+    ap.add_argument("--obs-cols", type=int, default=16)
     ap.add_argument("--partials", type=int, default=1, help="gae_stats: publish per-CTA partials (as inside the fused step)")
     ap.add_argument("--pipe", type=int, default=1, help="1: software-pipelined chunked scan, 0: two-phase")
     args = ap.parse_args()
@@ -72,6 +73,7 @@ def main():
     _lib.load().plb_set_tuning(3, args.obs_variant)
     _lib.load().plb_set_tuning(4, args.pipe)
     _lib.load().plb_set_tuning(5, args.debug)
+    _lib.load().plb_set_tuning(7, args.obs_cols)
     dev = torch.device("cuda:0")
     rng = np.random.default_rng(0)
     flush = torch.empty(256 * 2**20, dtype=torch.uint8, device=dev)  # > L2
