@@ -47,7 +47,7 @@ extern "C" {
 #define PLB_ERR_WORKSPACE (-3)
 
 /* scan algorithm selection */
-#define PLB_ALGO_AUTO 0
+#define PLB_ALGO_AUTO 0    /* chunked wherever the layout allows it (TMA alignment, inner == 1), else serial */
 #define PLB_ALGO_SERIAL 1  /* one thread per column, float64 step + float32 store: the
                               reference's per-step rounding, bit-identical to oracle/plb_oracle.c */
 #define PLB_ALGO_CHUNKED 2 /* TMA-staged chunked affine scan (float64 carries); |err| <= ~3e-6 */

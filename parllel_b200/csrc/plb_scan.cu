@@ -1035,9 +1035,9 @@ int scan_reverse(int mode, const float *reward, int64_t ld_r, const float *value
     if (fusion != nullptr && fusion->has_pre && fusion->reward_out != nullptr)
         can_chunk = can_chunk && tma_ok_f32(fusion->reward_out, fusion->ld_reward_out);
     if (algo == PLB_ALGO_AUTO) {
-        // the strict serial walk is memory-bound (and bit-exact) once there are enough columns
-        algo = (can_chunk && B * inner < 32768) ? PLB_ALGO_CHUNKED : PLB_ALGO_SERIAL;
-        if (fusion != nullptr && can_chunk) algo = PLB_ALGO_CHUNKED;
+        // the chunked scan is the faster one at every measured shape (C1: 13.5 us; C4: 49.8 us vs 53.8 us
+        // for the serial walk); PLB_ALGO_SERIAL stays available as the bit-exact (reference rounding) mode
+        algo = can_chunk ? PLB_ALGO_CHUNKED : PLB_ALGO_SERIAL;
     }
     if (algo == PLB_ALGO_CHUNKED) {
         PLB_REQUIRE(can_chunk, PLB_ERR_UNSUPPORTED,
@@ -1091,8 +1091,7 @@ int scan_forward(const float *reward, int64_t ld_r, const uint8_t *done, int64_t
     const bool can_chunk = scan_chunked_supported(reward, ld_r, nullptr, 0, done, ld_d, T, B, 1) &&
                            tma_ok_f32(out, ld_o);
     if (algo == PLB_ALGO_AUTO) {
-        algo = (can_chunk && B < 32768) ? PLB_ALGO_CHUNKED : PLB_ALGO_SERIAL;
-        if (fusion != nullptr && can_chunk) algo = PLB_ALGO_CHUNKED;
+        algo = can_chunk ? PLB_ALGO_CHUNKED : PLB_ALGO_SERIAL;
     }
     if (algo == PLB_ALGO_CHUNKED) {
         PLB_REQUIRE(can_chunk, PLB_ERR_UNSUPPORTED,

@@ -48,12 +48,21 @@ class NormalizeRewards(Transform):
         self.algo = self._ALGOS[algo]
         self._carry_return = None  # used only for leaves without padding
         self._carry_done = None
+        self._fused = None
 
     def __call__(self, sample_tree):
         reward_leaf = sample_tree["reward"]
         assert is_array_leaf(reward_leaf)
         assert batch_rank(reward_leaf) in (1, 2)
         past_leaf, done_leaf = sample_tree["past_return"], sample_tree["done"]
+        if (self.algo != _lib.ALGO_SERIAL and batch_rank(reward_leaf) == 2 and not self.return_statistics.sharded
+                and len(reward_leaf.shape) == 2):
+            # [T, B] batches take the fused chain's route: the past-return scan accumulates the moments and
+            # folds them into the running state in its tail, then one scaling pass (2 launches instead of 4)
+            if self._fused is None:
+                from .pipeline import FusedBatchTransforms
+                self._fused = FusedBatchTransforms([self])
+            return self._fused(sample_tree)
 
         st = Staging(self.return_statistics.device)
         reward = st.view(reward_leaf, writeback=True)

@@ -82,7 +82,9 @@ class FusedBatchTransforms(Transform):
 
     def __call__(self, sample_tree, phases: int = _lib.PHASE_ALL):
         # fast path: this tree was captured before and none of its leaves moved -> replay the graph
-        bound = self._bound.get((id(sample_tree), phases))
+        # inside somebody else's stream capture the launches are enqueued as they are (no nested graphs)
+        capturing = torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()
+        bound = None if capturing else self._bound.get((id(sample_tree), phases))
         if bound is not None:
             leaves, addresses, graph = bound
             if [self._address(leaf) for leaf in leaves] == addresses:
@@ -199,7 +201,7 @@ class FusedBatchTransforms(Transform):
                     nr._carry_done.copy_(done[T - 1])
 
         # the NCCL all-gathers of the sharded chain are captured into the graph as well
-        graphable = self.use_cuda_graph and not st.staged
+        graphable = self.use_cuda_graph and not st.staged and not capturing
         if not graphable:
             enqueue()
         else:
