@@ -132,6 +132,11 @@ def load() -> ctypes.CDLL:
         if sig is not None and hasattr(lib, name):
             fn = getattr(lib, name)
             fn.argtypes, fn.restype = sig
+    # experiments: PLB_TUNING="key=value,key=value" applies plb_set_tuning at load time
+    for item in filter(None, os.environ.get("PLB_TUNING", "").split(",")):
+        key, _, value = item.partition("=")
+        if lib.plb_set_tuning(int(key), int(value)) != 0:
+            raise PlbError(f"PLB_TUNING: bad item {item!r}")
     _lib = lib
     return lib
 
