@@ -882,6 +882,7 @@ bool scan_chunked_supported(const float *reward, int64_t ld_r, const float *valu
 static int g_chunked_geom = 0;
 static int g_chunked_f32 = 0;        // 1: float32 affine maps (fast variant)
 static int g_scan_debug = 0;
+static int g_scan_max_stages = 0;     // experiments: cap on the input ring depth (plb_set_tuning key 9)
 static int g_chunked_pipe = 1;       // 1: software-pipelined tile loop (default), 0: two-phase tile loop
 
 template <int MODE, typename ACC, int NW, int R, bool HAS_PRE, bool HAS_STATS>
@@ -917,6 +918,7 @@ static int launch_chunked_inst(const chunked::TensorMaps &tm, chunked::Params p,
         if (stages >= 2 || ctas_per_sm == 1) break;
     }
     if (stages > MAX_STAGES) stages = MAX_STAGES;
+    if (g_scan_max_stages > 0 && stages > g_scan_max_stages) stages = g_scan_max_stages;
     if (stages > p.n_chunks) stages = p.n_chunks;
     PLB_REQUIRE(stages >= 1, PLB_ERR_UNSUPPORTED, "chunked scan does not fit in shared memory");
     p.n_stages = stages;
@@ -1128,6 +1130,7 @@ int plb_set_tuning(int key, int value)
         case 1: plb::g_chunked_f32 = value; return PLB_OK;
         case 4: plb::g_chunked_pipe = value; return PLB_OK;
         case 5: plb::g_scan_debug = value; return PLB_OK;
+        case 9: plb::g_scan_max_stages = value; return PLB_OK;
         case 7: plb::set_obs_lsu_cols(value); return PLB_OK;
         case 3: plb::set_obs_variant(value); return PLB_OK;
         default: plb::set_error("unknown tuning key %d", key); return PLB_ERR_INVALID_ARGUMENT;
