@@ -302,6 +302,10 @@ typedef struct {
      * consumes it waits for all ranks and merges in rank order in its prologue.  `xch_peers` is the
      * DEVICE pointer table of plb_exchange_moments_p2p (buffers sized for n_vals = 3). */
     void *const *xch_peers; int32_t xch_rank, xch_world;
+    /* optional [B] buffers that receive past_return[T-1] / done[T-1] at the end of phase A -- the rows
+     * Array.rotate() (arrays/array.py:394-418) would copy into the padding for the next batch; for leaves
+     * without padding rows.  May alias previous_return / previous_done.  NULL = not wanted. */
+    float *carry_return_out; uint8_t *carry_done_out;
 } plb_batch_pipeline;
 
 PLB_API size_t plb_batch_pipeline_workspace_bytes(void);

@@ -50,6 +50,7 @@ class BatchPipeline(ctypes.Structure):
         ("moments_flags", c_int32),
         ("workspace", c_void_p), ("workspace_bytes", c_size_t),
         ("xch_peers", c_void_p), ("xch_rank", c_int32), ("xch_world", c_int32),
+        ("carry_return_out", c_void_p), ("carry_done_out", c_void_p),
     ]
 
 

@@ -80,6 +80,7 @@ static int run_pipeline(const plb_batch_pipeline *d, int phases, cudaStream_t st
             f.tail.upd_flags = d->moments_flags;
         }
         if (use_xch) f.tail.xch = xch;
+        f.carry_ret_out = d->carry_return_out; f.carry_done_out = d->carry_done_out;
         rc = scan_forward(d->reward, d->ld_reward, d->done, d->ld_done, d->previous_return, d->previous_done,
                           d->past_return, d->ld_past_return, T, B, d->discount, PLB_ALGO_CHUNKED, &f, stream);
         if (rc == PLB_OK && update_in_tail) state_updated = true;
@@ -93,8 +94,10 @@ static int run_pipeline(const plb_batch_pipeline *d, int phases, cudaStream_t st
             state_updated = true;
         }
         if (rc == PLB_ERR_UNSUPPORTED) {  // shape TMA cannot describe: serial scan + separate moments
+            ScanFusion fc = {};  // only the carry rows travel with the serial scan
+            fc.carry_ret_out = d->carry_return_out; fc.carry_done_out = d->carry_done_out;
             rc = scan_forward(d->reward, d->ld_reward, d->done, d->ld_done, d->previous_return, d->previous_done,
-                              d->past_return, d->ld_past_return, T, B, d->discount, PLB_ALGO_SERIAL, nullptr, stream);
+                              d->past_return, d->ld_past_return, T, B, d->discount, PLB_ALGO_SERIAL, &fc, stream);
             if (rc) return rc;
             rc = plb_batch_moments_f32(d->past_return, d->ld_past_return, T, B, d->valid, d->ld_valid,
                                        d->return_moments, ws_a, MOMENTS_WS_BYTES, stream);

@@ -214,6 +214,8 @@ struct Params {
     // optional fused moments of out0
     const uint8_t *valid; int64_t ld_valid;
     MomentsTail tail;
+    // forward scan, optional: out[T-1] and done[T-1] per column for the caller's carry rows
+    float *carry_ret_out; uint8_t *carry_done_out; const uint8_t *done_raw; int64_t ld_done_raw;
     int debug;                    // experiments only (plb_set_tuning key 5): 1 = skip the in-loop sums, 2 = skip the tail
 };
 
@@ -795,6 +797,15 @@ scan_pipelined_kernel(const __grid_constant__ TensorMaps tm, const Params p)
             sh->aggC[par][warp][lane] = c;
             if (MODE == 0 && warp == 0) sh->halo[par][lane] = vreg[0];
         }
+        if (MODE == 2 && P2 && p.carry_ret_out != nullptr && cu_k == n_chunks - 1) {
+            // the warp that holds t = T-1 hands the strip's last row to the caller's carry buffers
+            const int64_t r_last = T - 1 - cu_t0;
+            const int64_t ccol = (int64_t)cu_strip * W + lane;
+            if (r_last >= i0 && r_last < i0 + R && ccol < p.B) {
+                p.carry_ret_out[ccol] = O.o[0][r_last][lane];
+                p.carry_done_out[ccol] = p.done_raw[(T - 1) * p.ld_done_raw + ccol];
+            }
+        }
         if (P2) fence_proxy_async_smem();  // staging-tile writes -> visible to the TMA store issued after the next barrier
 
         // ---- advance the cursors ---------------------------------------------------------
@@ -1082,6 +1093,17 @@ int scan_reverse(int mode, const float *reward, int64_t ld_r, const float *value
     return PLB_OK;
 }
 
+// carry rows for callers without padding rows, when the scan kernel did not write them itself
+static int copy_carry_rows(const ScanFusion *fusion, const float *out, int64_t ld_o, const uint8_t *done, int64_t ld_d,
+                           int64_t T, int64_t B, cudaStream_t stream)
+{
+    if (fusion == nullptr || fusion->carry_ret_out == nullptr || fusion->carry_done_out == nullptr) return PLB_OK;
+    PLB_CUDA(cudaMemcpyAsync(fusion->carry_ret_out, out + (T - 1) * ld_o, (size_t)B * sizeof(float),
+                             cudaMemcpyDeviceToDevice, stream));
+    PLB_CUDA(cudaMemcpyAsync(fusion->carry_done_out, done + (T - 1) * ld_d, (size_t)B, cudaMemcpyDeviceToDevice, stream));
+    return PLB_OK;
+}
+
 int scan_forward(const float *reward, int64_t ld_r, const uint8_t *done, int64_t ld_d,
                  const float *prev_ret, const uint8_t *prev_done, float *out, int64_t ld_o,
                  int64_t T, int64_t B, double gamma, int algo, const ScanFusion *fusion, cudaStream_t stream)
@@ -1104,19 +1126,28 @@ int scan_forward(const float *reward, int64_t ld_r, const uint8_t *done, int64_t
         p.T = T; p.B = B;
         p.gamma = gamma; p.lambda = 1.0;
         p.clip_lo = -INFINITY; p.clip_hi = INFINITY;
+        bool carry_in_kernel = false;
         if (fusion != nullptr) {
             p.valid = fusion->valid; p.ld_valid = fusion->ld_valid;
             p.tail = fusion->tail;
+            if (fusion->carry_ret_out != nullptr && fusion->carry_done_out != nullptr && g_chunked_pipe != 0) {
+                p.carry_ret_out = fusion->carry_ret_out; p.carry_done_out = fusion->carry_done_out;
+                p.done_raw = done; p.ld_done_raw = ld_d;
+                carry_in_kernel = true;
+            }
         }
-        return launch_chunked<2>(io, p, false, stream);
+        const int rc = launch_chunked<2>(io, p, false, stream);
+        if (rc != PLB_OK || carry_in_kernel) return rc;
+        return copy_carry_rows(fusion, out, ld_o, done, ld_d, T, B, stream);
     }
     PLB_REQUIRE(algo == PLB_ALGO_SERIAL, PLB_ERR_INVALID_ARGUMENT, "unknown algo %d", algo);
-    PLB_REQUIRE(fusion == nullptr, PLB_ERR_UNSUPPORTED, "fused statistics need the chunked scan");
+    PLB_REQUIRE(fusion == nullptr || fusion->tail.moments_out == nullptr, PLB_ERR_UNSUPPORTED,
+                "fused statistics need the chunked scan");
     const int threads = 128;
     scan_forward_serial_kernel<<<(unsigned)ceil_div(B, threads), threads, 0, stream>>>(
         reward, ld_r, done, ld_d, prev_ret, prev_done, out, ld_o, T, B, gamma);
     PLB_LAUNCH_CHECK();
-    return PLB_OK;
+    return copy_carry_rows(fusion, out, ld_o, done, ld_d, T, B, stream);
 }
 
 }  // namespace plb

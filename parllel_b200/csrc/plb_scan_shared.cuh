@@ -63,6 +63,8 @@ struct ScanFusion {
     const uint8_t *valid;      // mask for the fused moments (nullptr = all)
     int64_t ld_valid;
     MomentsTail tail;          // fused moments of advantage / past_return
+    float *carry_ret_out;      // forward scan: receives out[T-1] per column (may alias prev_ret), or nullptr
+    uint8_t *carry_done_out;   // forward scan: receives done[T-1] per column (may alias prev_done), or nullptr
 };
 
 int scan_reverse(int mode, const float *reward, int64_t ld_r, const float *value, int64_t ld_v,

@@ -131,6 +131,10 @@ class FusedBatchTransforms(Transform):
             prev_ret, prev_done = prev_ret.reshape(-1).contiguous(), prev_done.reshape(-1).contiguous()
             keep += [prev_ret, prev_done]
             d.previous_return, d.previous_done = prev_ret.data_ptr(), prev_done.data_ptr()
+            if nr._carry_return is not None and nr._carry_done is not None:
+                # leaves without padding rows: phase A itself leaves past_return[T-1] / done[T-1] in the
+                # carry buffers (aliasing the previous rows is allowed)
+                d.carry_return_out, d.carry_done_out = nr._carry_return.data_ptr(), nr._carry_done.data_ptr()
             stats = nr.return_statistics
             d.return_mean, d.return_var = stats.mean_tensor.data_ptr(), stats.var_tensor.data_ptr()
             d.return_count = stats.count_tensor.data_ptr()
@@ -194,7 +198,7 @@ class FusedBatchTransforms(Transform):
                 _lib.check(lib.plb_batch_pipeline_f32(ctypes.byref(d), _lib.PHASE_C, s), "fused transforms (C)")
             else:
                 _lib.check(lib.plb_batch_pipeline_f32(ctypes.byref(d), phases, s), "fused transforms")
-            if nr is not None and T > 0:
+            if nr is not None and T > 0 and not (d.carry_return_out and d.carry_done_out):
                 if nr._carry_return is not None:
                     nr._carry_return.copy_(past[T - 1])
                 if nr._carry_done is not None:
