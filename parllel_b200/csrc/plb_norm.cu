@@ -139,7 +139,6 @@ normalize_advantage_partials_kernel(float *__restrict__ x, int64_t ld_x, int64_t
                                     const Sums *__restrict__ partials, const unsigned *__restrict__ n_partials,
                                     float eps, double *__restrict__ moments_out)
 {
-    __shared__ Sums scratch[32];
     __shared__ float s_mean, s_denom;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
@@ -162,12 +161,14 @@ normalize_advantage_partials_kernel(float *__restrict__ x, int64_t ld_x, int64_t
         const int64_t i = tid + (int64_t)u * nthreads;
         if (i < total) v[u] = *reinterpret_cast<const float4 *>(x + off[u]);
     }
-    const Moments m = reduce_published_partials(partials, *n_partials, scratch);
-    if (threadIdx.x == 0) {
-        s_mean = __double2float_rn(m.mean);
-        s_denom = __fadd_rn(__double2float_rn(sqrt(m.m2 / m.n)), eps);
-        if (blockIdx.x == 0) {
-            moments_out[0] = m.n; moments_out[1] = m.mean; moments_out[2] = m.m2;
+    if (threadIdx.x < 32) {  // one warp reduces the partial sums; the others go straight to the barrier
+        const Moments m = reduce_published_partials_warp(partials, *n_partials);
+        if (threadIdx.x == 0) {
+            s_mean = __double2float_rn(m.mean);
+            s_denom = __fadd_rn(__double2float_rn(sqrt(m.m2 / m.n)), eps);
+            if (blockIdx.x == 0) {
+                moments_out[0] = m.n; moments_out[1] = m.mean; moments_out[2] = m.m2;
+            }
         }
     }
     __syncthreads();

@@ -430,6 +430,37 @@ __device__ __forceinline__ Moments reduce_published_partials(const Sums *partial
     acc = block_reduce_sums(acc, scratch);
     return to_moments(acc);
 }
+// Same reduction by ONE warp (no block barrier inside): lanes take partials lane, lane+32, ... in index
+// order, rebase onto the first non-empty pivot of the warp, then plain shuffle adds.  Every lane returns
+// the same moments; summation order depends only on n.
+__device__ __forceinline__ Moments reduce_published_partials_warp(const Sums *partials, unsigned n)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    Sums acc;
+    acc.n = 0.0; acc.s1 = 0.0; acc.s2 = 0.0; acc.piv = 0.0;
+    for (unsigned i = lane; i < n; i += 32u) {
+        Sums q = partials[i];
+        if (q.n > 0.0) {
+            if (acc.n == 0.0) acc = q;
+            else {
+                q = rebase(q, acc.piv);
+                acc.n += q.n; acc.s1 += q.s1; acc.s2 += q.s2;
+            }
+        }
+    }
+    const unsigned has = __ballot_sync(0xffffffffu, acc.n > 0.0);
+    const int src = has ? (__ffs(has) - 1) : 0;
+    const double P = __shfl_sync(0xffffffffu, acc.piv, src);
+    acc = rebase(acc, P);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        acc.n += __shfl_xor_sync(0xffffffffu, acc.n, d);
+        acc.s1 += __shfl_xor_sync(0xffffffffu, acc.s1, d);
+        acc.s2 += __shfl_xor_sync(0xffffffffu, acc.s2, d);
+    }
+    acc.piv = P;
+    return to_moments(acc);
+}
 #endif  // __CUDACC__
 
 }  // namespace plb

@@ -14,7 +14,6 @@ Ring residency:
 """
 from __future__ import annotations
 
-import ctypes
 from typing import Callable, Iterator, Optional
 
 import numpy as np
