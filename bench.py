@@ -257,6 +257,25 @@ def measure_extras(dev, peak):
         out[f"estimate_advantage_T{T}_B{B}"] = {"us_per_launch": us, "transitions_per_s": T * B / us * 1e6,
                                                 "GB/s": 17 * T * B / us / 1e3, "frac_of_measured_peak": 17 * T * B / us / 1e3 / peak}
         del trees
+    # C0 (T=128, B=16: the reference's own CartPole PPO batch): launch-latency-bound, so report wall-clock
+    # microseconds per call of the public API (graph replay) instead of a roofline fraction
+    T, B = 128, 16
+    tree = ArrayDict({"reward": torch.randn(T, B, device=dev), "done": torch.rand(T, B, device=dev) < P_DONE,
+                      "agent_info": {"value": torch.randn(T, B, device=dev)}, "bootstrap_value": torch.randn(B, device=dev),
+                      "advantage": torch.empty(T, B, device=dev), "return_": torch.empty(T, B, device=dev),
+                      "past_return": torch.empty(T, B, device=dev)})
+    chain = FusedBatchTransforms([NormalizeRewards(tree, GAMMA), ClipRewards(-5, 5),
+                                  EstimateAdvantage(GAMMA, LAMBDA), NormalizeAdvantage(tree)])
+    for _ in range(10):
+        chain(tree)
+    torch.cuda.synchronize()
+    n = 2000
+    t0 = time.perf_counter()
+    for _ in range(n):
+        chain(tree)
+    torch.cuda.synchronize()
+    out["full_chain_T128_B16"] = {"us_per_call_wall": (time.perf_counter() - t0) / n * 1e6, "bound": "launch latency",
+                                  "api": "FusedBatchTransforms(4 transforms)(tree), CUDA-graph replay, device leaves"}
     return out
 
 
