@@ -383,20 +383,23 @@ def main():
         for i in range(n_sets):
             raw(sets[i], phases=_lib.PHASE_B | _lib.PHASE_PARTIALS)
         torch.cuda.synchronize()
+        # >= 20 launches per graph so that the ~2.7 us device-side gap between two graph launches is not
+        # charged to the kernel (CUDA event resolution is ~2 us as well)
+        per_graph = n_sets * max(1, -(-20 // n_sets))
         kgraph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(kgraph):
-            for i in range(n_sets):
-                raw(sets[i], phases=_lib.PHASE_B | _lib.PHASE_PARTIALS)
+            for i in range(per_graph):
+                raw(sets[i % n_sets], phases=_lib.PHASE_B | _lib.PHASE_PARTIALS)
         kgraph.replay()
         torch.cuda.synchronize()
-        n_replays = max(1, args.steps // n_sets)
+        n_replays = max(1, args.steps // per_graph)
         k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         k0.record(stream)
         for _ in range(n_replays):
             kgraph.replay()
         k1.record(stream)
         torch.cuda.synchronize()
-        kernel_launches = n_replays * n_sets
+        kernel_launches = n_replays * per_graph
         gae_us = k0.elapsed_time(k1) * 1e3 / kernel_launches
 
         # keep the GPU under the same load for a few clock samples (a FIXED number of extra steps: with
