@@ -69,10 +69,22 @@ PLB_API int plb_sm_count(void);
 /* Tuning / diagnostics knobs (process-wide; used by tools/ and the tests, not by the transforms).
  *   key 0: tile geometry of the chunked scan: 0 auto, 1 = 8 warps x 8 rows, 2 = 8 x 16, 3 = 16 x 8
  *   key 1: 1 = float32 affine maps in the chunked scan (default 0 = float64)
- *   key 3: NormalizeObservations step kernel: 0 auto, 1 shared-memory slab (TMA), 2 two-pass L2 slab */
+ *   key 3: NormalizeObservations step kernel: 0 auto (4, then 1, then 2, then three kernels),
+ *          1 shared-memory slab through TMA, 2 two-pass L2 slab, 3 two-CTA cluster slab,
+ *          4 shared-memory slab through cp.async / direct stores
+ *   key 4: 1 (default) software-pipelined tile loop of the chunked scan, 0 two-phase loop
+ *   key 5: experiments only: 1 skip the fused statistics, 2 skip their tail (results then incomplete)
+ *   key 7: slab width of observation variant 4: 8, 16 (default) or 32 columns
+ *   key 9: cap on the input ring depth of the chunked scan (0 = as many stages as fit)
+ * The environment variable PLB_TUNING="key=value,..." applies them when the Python package loads
+ * the library. */
 #define PLB_TUNE_CHUNK_GEOMETRY 0
 #define PLB_TUNE_CHUNK_F32 1
-#define PLB_TUNE_SCAN_PIPELINED 4   /* 1 (default): software-pipelined tile loop; 0: two-phase loop */
+#define PLB_TUNE_OBS_VARIANT 3
+#define PLB_TUNE_SCAN_PIPELINED 4
+#define PLB_TUNE_SCAN_DEBUG 5
+#define PLB_TUNE_OBS_SLAB_COLS 7
+#define PLB_TUNE_SCAN_MAX_STAGES 9
 PLB_API int plb_set_tuning(int key, int value);
 
 /* ------------------------------------------------------------------------------------
