@@ -58,6 +58,11 @@ elementwise_kernel(float *__restrict__ x, int64_t ld_x, int64_t rows, int64_t co
     }
 }
 
+// grid cap of the streaming elementwise kernels, in CTAs of 256 threads per SM (C1 step: 21.0 us with 4,
+// 22.0 with 8, 22.4 with 2); plb_set_tuning key 11
+static int g_normadv_ctas_per_sm = 4;
+void set_normadv_ctas_per_sm(int v) { g_normadv_ctas_per_sm = v > 0 ? v : 4; }
+
 template <class F>
 static int launch_elementwise(float *x, int64_t ld_x, int64_t rows, int64_t cols, bool col_dependent, F f,
                               cudaStream_t stream)
@@ -74,7 +79,7 @@ static int launch_elementwise(float *x, int64_t ld_x, int64_t rows, int64_t cols
     PLB_REQUIRE(sms > 0, PLB_ERR_UNSUPPORTED, "no CUDA device");
     int64_t blocks = ceil_div(vec ? total / 4 : total, 256 * 4);
     if (blocks < 1) blocks = 1;
-    if (blocks > (int64_t)sms * 16) blocks = (int64_t)sms * 16;
+    if (blocks > (int64_t)sms * g_normadv_ctas_per_sm) blocks = (int64_t)sms * g_normadv_ctas_per_sm;
     if (vec) elementwise_kernel<true, F><<<(unsigned)blocks, 256, 0, stream>>>(x, ld_x, rows, cols, f);
     else elementwise_kernel<false, F><<<(unsigned)blocks, 256, 0, stream>>>(x, ld_x, rows, cols, f);
     PLB_LAUNCH_CHECK();
@@ -276,7 +281,7 @@ int normalize_advantage_after_exchange(float *x, int64_t ld_x, int64_t rows, int
     PLB_REQUIRE(sms > 0, PLB_ERR_UNSUPPORTED, "no CUDA device");
     int64_t blocks = ceil_div(rows * cols / 4, 256 * 4);
     if (blocks < 1) blocks = 1;
-    if (blocks > (int64_t)sms * 8) blocks = (int64_t)sms * 8;
+    if (blocks > (int64_t)sms * g_normadv_ctas_per_sm) blocks = (int64_t)sms * g_normadv_ctas_per_sm;
     normalize_advantage_xch_kernel<<<(unsigned)blocks, 256, 0, stream>>>(x, ld_x, rows, cols, xch, (float)eps, moments_out);
     PLB_LAUNCH_CHECK();
     return PLB_OK;
@@ -297,7 +302,7 @@ int normalize_advantage_from_partials(float *x, int64_t ld_x, int64_t rows, int6
     PLB_REQUIRE(sms > 0, PLB_ERR_UNSUPPORTED, "no CUDA device");
     int64_t blocks = ceil_div(rows * cols / 4, 256 * 4);
     if (blocks < 1) blocks = 1;
-    if (blocks > (int64_t)sms * 8) blocks = (int64_t)sms * 8;
+    if (blocks > (int64_t)sms * g_normadv_ctas_per_sm) blocks = (int64_t)sms * g_normadv_ctas_per_sm;
     const MomentsTail t = make_tail(moments_out, tail_workspace);
     // (programmatic dependent launch of this kernel behind the scan was measured: no gain, 22.3 us either way)
     normalize_advantage_partials_kernel<<<(unsigned)blocks, 256, 0, stream>>>(x, ld_x, rows, cols, t.partials,

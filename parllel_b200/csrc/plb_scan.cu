@@ -1162,6 +1162,7 @@ int plb_set_tuning(int key, int value)
         case 4: plb::g_chunked_pipe = value; return PLB_OK;
         case 5: plb::g_scan_debug = value; return PLB_OK;
         case 9: plb::g_scan_max_stages = value; return PLB_OK;
+        case 11: plb::set_normadv_ctas_per_sm(value); return PLB_OK;
         case 7: plb::set_obs_lsu_cols(value); return PLB_OK;
         case 3: plb::set_obs_variant(value); return PLB_OK;
         default: plb::set_error("unknown tuning key %d", key); return PLB_ERR_INVALID_ARGUMENT;

@@ -83,6 +83,7 @@ int column_moments(const float *x, int64_t ld_x, int64_t rows, int64_t cols, con
                    void *workspace, size_t workspace_bytes, cudaStream_t stream);
 int obs_variant();
 void set_obs_variant(int v);
+void set_normadv_ctas_per_sm(int v);
 void set_obs_lsu_cols(int v);
 int obs_step_two_pass_l2(float *x, int64_t ld, int64_t rows, int64_t cols, const uint8_t *row_valid,
                          double *mean, double *var, const double *count, double *batch_count_out,
