@@ -24,7 +24,10 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC,-fvisibility=hidden,-O3",
     "-Xptxas", "-v",
     "--expt-relaxed-constexpr", "--extended-lambda",
-    "-shared", "-cudart", "static",
+    # shared CUDA runtime: the process (torch) already maps libcudart.so.12, and a statically linked
+    # runtime would bake every cudart entry-point name into the artefact
+    "-shared", "-cudart", "shared",
+    "-Xlinker", "-rpath,/usr/local/cuda/lib64",
 ]
 
 
