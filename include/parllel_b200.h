@@ -39,7 +39,7 @@ extern "C" {
 #define PLB_API
 #endif
 
-#define PLB_VERSION 100 /* 0.1.0 */
+#define PLB_VERSION 200 /* 0.2.0 */
 
 #define PLB_OK 0
 #define PLB_ERR_INVALID_ARGUMENT (-1)
@@ -64,27 +64,31 @@ typedef void *plb_stream_t; /* cudaStream_t */
 
 PLB_API int plb_version(void);
 PLB_API const char *plb_last_error(void);
+/* Kernels this process has ENQUEUED through the library so far (launches recorded into a CUDA graph
+ * under capture count once, at capture): out2[0] = all kernels, out2[1] = resident advantage kernels. */
+PLB_API void plb_launch_counters(int64_t *out2);
 /* Number of SMs of the current device (grid sizing); <0 on error. */
 PLB_API int plb_sm_count(void);
 /* Tuning / diagnostics knobs (process-wide; used by tools/ and the tests, not by the transforms).
- *   key 0: tile geometry of the chunked scan: 0 auto, 1 = 8 warps x 8 rows, 2 = 8 x 16, 3 = 16 x 8
- *   key 1: 1 = float32 affine maps in the chunked scan (default 0 = float64)
+ *   key 0: tile geometry of the chunked scan: 0 auto, 1 = 8 warps x 8 rows, 2 = 8 warps x 16 rows
  *   key 3: NormalizeObservations step kernel: 0 auto (4, then 1, then 2, then three kernels),
  *          1 shared-memory slab through TMA, 2 two-pass L2 slab, 3 two-CTA cluster slab,
  *          4 shared-memory slab through cp.async / direct stores
- *   key 4: 1 (default) software-pipelined tile loop of the chunked scan, 0 two-phase loop
- *   key 5: experiments only: 1 skip the fused statistics, 2 skip their tail (results then incomplete)
+ *   key 5: experiments only: 1 skip the fused statistics, 2 skip their tail (results then incomplete),
+ *          4 resident kernel: final advantage through plain stores instead of per-warp TMA stores
  *   key 7: slab width of observation variant 4: 8, 16 (default) or 32 columns
  *   key 9: cap on the input ring depth of the chunked scan (0 = as many stages as fit)
+ *   key 11: grid cap of the streaming normalise kernels, CTAs of 256 threads per SM (default 4)
+ *   key 12: 0 = never take the resident (tensor-memory) advantage kernel (default 1)
  * The environment variable PLB_TUNING="key=value,..." applies them when the Python package loads
  * the library. */
 #define PLB_TUNE_CHUNK_GEOMETRY 0
-#define PLB_TUNE_CHUNK_F32 1
 #define PLB_TUNE_OBS_VARIANT 3
-#define PLB_TUNE_SCAN_PIPELINED 4
 #define PLB_TUNE_SCAN_DEBUG 5
 #define PLB_TUNE_OBS_SLAB_COLS 7
 #define PLB_TUNE_SCAN_MAX_STAGES 9
+#define PLB_TUNE_NORMADV_CTAS_PER_SM 11
+#define PLB_TUNE_RESIDENT 12
 PLB_API int plb_set_tuning(int key, int value);
 
 /* ------------------------------------------------------------------------------------
@@ -318,10 +322,36 @@ typedef struct {
      * Array.rotate() (arrays/array.py:394-418) would copy into the padding for the next batch; for leaves
      * without padding rows.  May alias previous_return / previous_done.  NULL = not wanted. */
     float *carry_return_out; uint8_t *carry_done_out;
+    /* optional: grid-exchange buffers (plb_grid_exchange_bytes) of every rank as a DEVICE pointer table
+     * [gx_world]; on one GPU a table with the single local buffer.  With them, EstimateAdvantage +
+     * NormalizeAdvantage (norm_advantage.py:30-56 after advantage.py:91-106) run as ONE cooperative
+     * launch wherever the batch allows it (PLB_PLAN_RESIDENT): the advantage waits in tensor memory while
+     * every CTA of every rank exchanges its partial moments through these buffers, and is written once,
+     * normalised.  `gx_slots` = records per rank (plb_grid_exchange_slots(), identical on all ranks). */
+    void *const *gx_peers; int32_t gx_rank, gx_world, gx_slots;
+    /* which fused routes the call may take: PLB_PLAN_AUTO on one GPU; on several GPUs the bitwise AND over
+     * all ranks of plb_batch_pipeline_plan(), so that every rank takes the same exchange protocol */
+    int32_t plan;
 } plb_batch_pipeline;
+
+#define PLB_PLAN_AUTO (-1)
+#define PLB_PLAN_CHUNKED 1  /* both scans can run as TMA-staged chunked scans (in-kernel moment exchange possible) */
+#define PLB_PLAN_RESIDENT 2 /* EstimateAdvantage + NormalizeAdvantage fit the single-launch resident kernel */
 
 PLB_API size_t plb_batch_pipeline_workspace_bytes(void);
 PLB_API int plb_batch_pipeline_f32(const plb_batch_pipeline *desc, int phases, plb_stream_t stream);
+/* Which fused routes THIS rank's leaves allow (PLB_PLAN_* bits; >= 0).  Pure host-side inspection of
+ * the descriptor (shapes, alignment, strides); nothing is enqueued. */
+PLB_API int plb_batch_pipeline_plan(const plb_batch_pipeline *desc);
+
+/* Grid-exchange buffers of the resident kernel: `slots` = plb_grid_exchange_slots() records per rank;
+ * a buffer is plb_grid_exchange_bytes(world, slots) long, zero-filled ONCE, and (for world > 1) mapped
+ * into every peer (e.g. torch symmetric memory).  All ranks must issue the same sequence of calls on one
+ * buffer set.  plb_grid_exchange_status copies the status word back (synchronises `stream`):
+ * 0 = ok, 1 = a launch timed out waiting for a peer (its results are NaN), <0 = library error. */
+PLB_API int plb_grid_exchange_slots(void);
+PLB_API size_t plb_grid_exchange_bytes(int32_t world, int32_t slots);
+PLB_API int plb_grid_exchange_status(const void *local_buffer, plb_stream_t stream);
 
 #ifdef __cplusplus
 }

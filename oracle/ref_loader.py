@@ -7,7 +7,7 @@ the ``-m "not gpu"`` tests that pin the oracle against the live reference.
 
 The only import the reference needs that this image lacks is ``gymnasium``
 (type names + ``gymnasium.utils.colorize``, parllel/logger/logger.py:11); the
-stub package in ``oracle/gymnasium_stub`` satisfies it.
+stub package in ``baseline/gymnasium_stub`` satisfies it.
 """
 from __future__ import annotations
 
@@ -15,7 +15,7 @@ import os
 import sys
 
 REFERENCE_ROOT = os.environ.get("PLB_REFERENCE_ROOT", "/root/reference")
-_STUB = os.path.join(os.path.dirname(os.path.abspath(__file__)), "gymnasium_stub")
+_STUB = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "gymnasium_stub")
 
 
 def reference_available() -> bool:

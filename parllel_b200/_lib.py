@@ -51,16 +51,20 @@ class BatchPipeline(ctypes.Structure):
         ("workspace", c_void_p), ("workspace_bytes", c_size_t),
         ("xch_peers", c_void_p), ("xch_rank", c_int32), ("xch_world", c_int32),
         ("carry_return_out", c_void_p), ("carry_done_out", c_void_p),
+        ("gx_peers", c_void_p), ("gx_rank", c_int32), ("gx_world", c_int32), ("gx_slots", c_int32),
+        ("plan", c_int32),
     ]
 
 
 PHASE_A, PHASE_B, PHASE_C, PHASE_ALL = 1, 2, 4, 7
 PHASE_PARTIALS = 8  # modifier: B and C issued by separate calls, statistics travel as per-CTA partials
+PLAN_AUTO, PLAN_CHUNKED, PLAN_RESIDENT = -1, 1, 2
 
 _SIGNATURES = {
     "plb_version": ([], c_int),
     "plb_last_error": ([], ctypes.c_char_p),
     "plb_sm_count": ([], c_int),
+    "plb_launch_counters": ([ctypes.POINTER(c_int64)], None),
     "plb_set_tuning": ([c_int, c_int], c_int),
     "plb_compute_gae_advantage_f32": (
         [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64,
@@ -103,10 +107,11 @@ _SIGNATURES = {
         [c_void_p, c_int64, c_int64, c_int64, c_int, c_int64, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p], c_int),
     "plb_batch_pipeline_workspace_bytes": ([], c_size_t),
     "plb_batch_pipeline_f32": ([ctypes.POINTER(BatchPipeline), c_int, c_void_p], c_int),
+    "plb_batch_pipeline_plan": ([ctypes.POINTER(BatchPipeline)], c_int),
+    "plb_grid_exchange_slots": ([], c_int),
+    "plb_grid_exchange_bytes": ([c_int32, c_int32], c_size_t),
+    "plb_grid_exchange_status": ([c_void_p, c_void_p], c_int),
 }
-
-# entry points added after the first release are bound when present (see include/parllel_b200.h)
-_OPTIONAL = {}
 
 _lib = None
 
@@ -129,10 +134,6 @@ def load() -> ctypes.CDLL:
         fn = getattr(lib, name)  # AttributeError here = header/library mismatch: fail loudly
         fn.argtypes = argtypes
         fn.restype = restype
-    for name, sig in _OPTIONAL.items():
-        if sig is not None and hasattr(lib, name):
-            fn = getattr(lib, name)
-            fn.argtypes, fn.restype = sig
     # experiments: PLB_TUNING="key=value,key=value" applies plb_set_tuning at load time
     for item in filter(None, os.environ.get("PLB_TUNING", "").split(",")):
         key, _, value = item.partition("=")
@@ -148,6 +149,13 @@ def check(rc: int, what: str = "") -> None:
         msg = msg.decode("utf-8", "replace") if msg else ""
         kind = "CUDA error" if rc > 0 else "library error"
         raise PlbError(f"{what or 'libparllel_b200'}: {kind} {rc}: {msg}")
+
+
+def launch_counters() -> tuple[int, int]:
+    """(kernels enqueued by the library so far, of which resident advantage kernels)."""
+    out = (c_int64 * 2)()
+    load().plb_launch_counters(out)
+    return int(out[0]), int(out[1])
 
 
 def exported_symbols() -> list[str]:

@@ -15,6 +15,13 @@ void set_error(const char *fmt, ...)
     va_end(ap);
 }
 
+static long long g_launches = 0, g_resident_launches = 0;  // enqueued by this process (any thread)
+void count_launch(int resident)
+{
+    __atomic_add_fetch(&g_launches, 1, __ATOMIC_RELAXED);
+    if (resident) __atomic_add_fetch(&g_resident_launches, 1, __ATOMIC_RELAXED);
+}
+
 int sm_count()
 {
     static thread_local int cached_dev = -1;
@@ -37,6 +44,13 @@ extern "C" {
 int plb_version(void) { return PLB_VERSION; }
 
 const char *plb_last_error(void) { return plb::g_last_error; }
+
+void plb_launch_counters(int64_t *out2)
+{
+    if (out2 == nullptr) return;
+    out2[0] = __atomic_load_n(&plb::g_launches, __ATOMIC_RELAXED);
+    out2[1] = __atomic_load_n(&plb::g_resident_launches, __ATOMIC_RELAXED);
+}
 
 int plb_sm_count(void)
 {

@@ -36,7 +36,13 @@ void set_error(const char *fmt, ...);
         }                                                                                \
     } while (0)
 
-#define PLB_LAUNCH_CHECK() PLB_CUDA(cudaGetLastError())
+// every kernel launch site ends with PLB_LAUNCH_CHECK(): it also feeds plb_launch_counters()
+void count_launch(int resident);
+#define PLB_LAUNCH_CHECK()          \
+    do {                            \
+        ::plb::count_launch(0);     \
+        PLB_CUDA(cudaGetLastError()); \
+    } while (0)
 
 int sm_count();  // cached per device
 

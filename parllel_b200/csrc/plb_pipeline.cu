@@ -62,7 +62,19 @@ static int run_pipeline(const plb_batch_pipeline *d, int phases, cudaStream_t st
     const bool use_xch = (phases == PLB_PHASE_ALL) && xch.peers != nullptr && xch.world > 1;
     PLB_REQUIRE(!use_xch || (xch.world <= 32 && xch.rank >= 0 && xch.rank < xch.world), PLB_ERR_INVALID_ARGUMENT,
                 "in-kernel exchange supports up to 32 ranks");
+    // the in-kernel exchange only exists in the chunked scans: every rank must be able to take them, which
+    // the caller establishes by AND-ing plb_batch_pipeline_plan() over the ranks (uneven shards may differ)
+    PLB_REQUIRE(!use_xch || (d->plan != PLB_PLAN_AUTO && (d->plan & PLB_PLAN_CHUNKED)), PLB_ERR_INVALID_ARGUMENT,
+                "in-kernel exchange needs an agreed plan with PLB_PLAN_CHUNKED (see plb_batch_pipeline_plan)");
     bool adv_pushed = false;
+    // EstimateAdvantage + NormalizeAdvantage as one cooperative launch (advantage resident in tensor memory)
+    const int plan = d->plan;
+    GridXch gx;
+    gx.peers = reinterpret_cast<unsigned char *const *>(d->gx_peers);
+    gx.rank = d->gx_rank; gx.world = d->gx_world; gx.slots = d->gx_slots;
+    const bool want_resident = est_adv && norm_adv && (phases & PLB_PHASE_B) && (phases & PLB_PHASE_C) && !split_partials &&
+                               gx.peers != nullptr && (plan & PLB_PLAN_RESIDENT) &&
+                               (gx.world > 1 ? plan != PLB_PLAN_AUTO : true);
     const bool update_in_tail = (phases == PLB_PHASE_ALL) && norm_rew && !use_xch;
     bool state_updated = false;
 
@@ -93,6 +105,7 @@ static int run_pipeline(const plb_batch_pipeline *d, int phases, cudaStream_t st
             if (rc) return rc;
             state_updated = true;
         }
+        if (rc == PLB_ERR_UNSUPPORTED && use_xch) return rc;  // agreed plan broken: never switch protocol alone
         if (rc == PLB_ERR_UNSUPPORTED) {  // shape TMA cannot describe: serial scan + separate moments
             ScanFusion fc = {};  // only the carry rows travel with the serial scan
             fc.carry_ret_out = d->carry_return_out; fc.carry_done_out = d->carry_done_out;
@@ -137,12 +150,33 @@ static int run_pipeline(const plb_batch_pipeline *d, int phases, cudaStream_t st
                 if (use_xch) f.tail.xch = xch;
             }
             const int mode = (d->gae_lambda == 1.0) ? 1 : 0;
+            const bool resident = want_resident &&
+                                  resident_supported(d->reward, d->ld_reward, d->value, d->ld_value, d->done, d->ld_done,
+                                                     d->advantage, d->ld_advantage, d->return_, d->ld_return, T, B) &&
+                                  (!has_pre || (aligned(d->reward, 16) && d->ld_reward % 4 == 0));
+            // several GPUs: the route was agreed through `plan`; a rank that cannot follow must not pick another
+            PLB_REQUIRE(resident || !(want_resident && gx.world > 1), PLB_ERR_UNSUPPORTED,
+                        "plan includes PLB_PLAN_RESIDENT but this rank's leaves do not allow it");
+            if (resident) {
+                ScanFusion fr = f;
+                fr.tail = make_tail(d->advantage_moments, ws_b);
+                fr.resident = 1;
+                fr.gx = gx;
+                fr.adv_eps = d->eps_advantage;
+                fr.adv_moments_out = d->advantage_moments;
+                rc = scan_reverse(mode, d->reward, d->ld_reward, d->value, d->ld_value, d->done, d->ld_done,
+                                  d->bootstrap_value, d->advantage, d->ld_advantage, d->return_, d->ld_return,
+                                  T, B, 1, d->discount, d->gae_lambda, PLB_ALGO_CHUNKED, &fr, stream);
+                if (rc) return rc;
+                return PLB_OK;  // phases B and C are complete
+            }
             rc = scan_reverse(mode, d->reward, d->ld_reward, d->value, d->ld_value, d->done, d->ld_done,
                               d->bootstrap_value, d->advantage, d->ld_advantage, d->return_, d->ld_return,
                               T, B, 1, d->discount, d->gae_lambda, PLB_ALGO_CHUNKED,
                               (has_pre || norm_adv) ? &f : nullptr, stream);
             if (rc == PLB_OK && norm_adv && direct_partials) adv_partials_published = true;
             if (rc == PLB_OK && norm_adv && use_xch) adv_pushed = true;
+            if (rc == PLB_ERR_UNSUPPORTED && use_xch) return rc;
             if (rc == PLB_ERR_UNSUPPORTED) {  // unfused fallback, same results
                 if (has_pre) {
                     rc = plb_scale_clip_f32(d->reward, d->ld_reward, T, B, f.reward_var, d->eps_reward, lo, hi, stream);
@@ -205,11 +239,60 @@ static int run_pipeline(const plb_batch_pipeline *d, int phases, cudaStream_t st
     return PLB_OK;
 }
 
+// host-side inspection: which fused routes do this rank's leaves allow?
+static int pipeline_plan(const plb_batch_pipeline *d)
+{
+    PLB_REQUIRE(d != nullptr, PLB_ERR_INVALID_ARGUMENT, "null descriptor");
+    if (d->T <= 0 || d->B <= 0) return PLB_PLAN_CHUNKED | PLB_PLAN_RESIDENT;  // nothing to do: follows any route
+    int plan = 0;
+    const bool fwd_ok = !d->normalize_rewards ||
+                        (scan_chunked_supported(d->reward, d->ld_reward, nullptr, 0, d->done, d->ld_done, d->T, d->B, 1) &&
+                         aligned(d->past_return, 16) && d->ld_past_return % 4 == 0);
+    const bool rev_ok = !d->estimate_advantage ||
+                        (scan_chunked_supported(d->reward, d->ld_reward, d->value, d->ld_value, d->done, d->ld_done, d->T, d->B, 1) &&
+                         aligned(d->advantage, 16) && d->ld_advantage % 4 == 0 && aligned(d->return_, 16) && d->ld_return % 4 == 0);
+    const bool adv_vec = !d->normalize_advantage ||
+                         (aligned(d->advantage, 16) && d->ld_advantage % 4 == 0 && (d->ld_advantage == d->B ? (d->T * d->B) % 4 == 0 : d->B % 4 == 0));
+    if (fwd_ok && rev_ok && adv_vec) plan |= PLB_PLAN_CHUNKED;
+    if (d->estimate_advantage && d->normalize_advantage && rev_ok &&
+        resident_supported(d->reward, d->ld_reward, d->value, d->ld_value, d->done, d->ld_done, d->advantage, d->ld_advantage,
+                           d->return_, d->ld_return, d->T, d->B))
+        plan |= PLB_PLAN_RESIDENT;
+    return plan;
+}
+
 }  // namespace plb
 
 extern "C" {
 
 size_t plb_batch_pipeline_workspace_bytes(void) { return 2 * plb::MOMENTS_WS_BYTES; }
+
+int plb_batch_pipeline_plan(const plb_batch_pipeline *desc) { return plb::pipeline_plan(desc); }
+
+int plb_grid_exchange_slots(void)
+{
+    const int sms = plb::sm_count();
+    if (sms <= 0) { plb::set_error("no CUDA device available"); return PLB_ERR_UNSUPPORTED; }
+    return sms < plb::GX_MAX_SLOTS ? sms : plb::GX_MAX_SLOTS;
+}
+
+size_t plb_grid_exchange_bytes(int32_t world, int32_t slots)
+{
+    if (world < 1 || world > plb::GX_MAX_WORLD || slots < 1 || slots > plb::GX_MAX_SLOTS) return 0;
+    return plb::gx_total_bytes(world, slots);
+}
+
+int plb_grid_exchange_status(const void *local_buffer, plb_stream_t stream)
+{
+    using namespace plb;
+    PLB_REQUIRE(local_buffer != nullptr, PLB_ERR_INVALID_ARGUMENT, "null buffer");
+    uint32_t status = 0;
+    PLB_CUDA(cudaMemcpyAsync(&status, reinterpret_cast<const unsigned char *>(local_buffer) + 8, sizeof(status),
+                             cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    PLB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    if (status != 0) set_error("grid exchange timed out waiting for a peer rank (results of that launch are NaN)");
+    return (int)status;
+}
 
 int plb_batch_pipeline_f32(const plb_batch_pipeline *desc, int phases, plb_stream_t stream)
 {

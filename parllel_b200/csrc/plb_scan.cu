@@ -217,6 +217,13 @@ struct Params {
     // forward scan, optional: out[T-1] and done[T-1] per column for the caller's carry rows
     float *carry_ret_out; uint8_t *carry_done_out; const uint8_t *done_raw; int64_t ld_done_raw;
     int debug;                    // experiments only (plb_set_tuning key 5): 1 = skip the in-loop sums, 2 = skip the tail
+    // resident variant (NormalizeAdvantage fused into the reverse scan)
+    GridXch gx;
+    float adv_eps;
+    double *adv_moments_out;
+    float *out0_raw; int64_t ld_out0_raw;   // out0 as a plain pointer (ragged rows of the final store phase)
+    int tmem_cols;                // TMEM columns to allocate: power of two >= tiles per CTA x 2 x R
+    int n_out_bufs;               // staging buffers of the final store phase carved from the input ring (2 or 4)
 };
 
 struct TensorMaps {
@@ -226,306 +233,48 @@ struct TensorMaps {
     // negative row.  TMA loads zero-fill there, but a TMA STORE may not start out of bounds:
     // that ragged tile is stored through maps whose box is only T % TC rows tall, from row 0.
     CUtensorMap o0_rag, o1_rag, o2_rag;
+    // resident variant: out0 with a box of one warp's R rows (every warp stores its own slab)
+    CUtensorMap o0_warp;
 };
 
 __device__ __forceinline__ float to_f32(double x) { return __double2float_rn(x); }
 __device__ __forceinline__ float to_f32(float x) { return x; }
 
 // MODE 0: GAE, 1: discounted return (both reverse), 2: past return (forward).
-// ACC: arithmetic type of the affine maps (double = default; float = fast variant).
+// ACC: arithmetic type of the affine maps (double; a float variant measured only ~4 % faster and was removed).
 // Output slots: MODE 0: o0 = advantage, o1 = return_; MODE 1: same; MODE 2: o0 = past_return;
 //               HAS_PRE adds the transformed reward as the last slot.
-template <int MODE, typename ACC, int NW, int R, bool HAS_PRE, bool HAS_STATS>
-__global__ void __launch_bounds__(NW * 32)
-scan_chunked_kernel(const __grid_constant__ TensorMaps tm, const Params p)
-{
-    constexpr int TC = NW * R;
-    constexpr int NWARPS = NW;
-    constexpr bool REVERSE = (MODE != 2);
-    constexpr int N_OUT = (REVERSE ? 2 : 1) + (HAS_PRE ? 1 : 0);
-    constexpr int PRE_SLOT = N_OUT - 1;
-    constexpr uint32_t TX_BYTES = REVERSE ? (sizeof(float) * TC * W * 2 + TC * W) : (sizeof(float) * TC * W + TC * W);
-    using StageT = Stage<TC>;
-    using OutT = OutTile<TC, N_OUT>;
-    using SharedT = Shared<ACC, NW>;
-
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    StageT *stages = reinterpret_cast<StageT *>(smem_raw);
-    OutT *outs = reinterpret_cast<OutT *>(smem_raw + sizeof(StageT) * p.n_stages);
-    SharedT *sh = reinterpret_cast<SharedT *>(smem_raw + sizeof(StageT) * p.n_stages + 2 * sizeof(OutT));
-    __shared__ Sums red_scratch[32];
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_stages = p.n_stages, n_chunks = p.n_chunks, n_strips = p.n_strips;
-    const int64_t T = p.T;
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < n_stages; ++s) mbar_init(&sh->full[s], 1);
-        fence_proxy_async_smem();  // barrier inits (generic proxy) -> visible to the TMA (async proxy)
-    }
-    __syncthreads();
-
-    // ---- producer state (thread 0 only): next tile to request -------------------------
-    int iss_strip = blockIdx.x, iss_chunk = 0, iss_stage = 0;
-    auto issue_one = [&]() {
-        const int c0 = iss_strip * W;
-        const int t0 = REVERSE ? (int)T - (iss_chunk + 1) * TC : iss_chunk * TC;
-        unsigned long long *bar = &sh->full[iss_stage];
-        StageT &S = stages[iss_stage];
-        mbar_arrive_expect_tx(bar, TX_BYTES);
-        tma_load_2d(&S.r[0][0], &tm.r, c0, t0, bar);
-        if (REVERSE) {
-            tma_load_2d(&S.v[0][0], &tm.v, c0, t0, bar);
-            tma_load_2d(&S.d[0][0], &tm.d, c0, t0, bar);
-        } else {
-            tma_load_2d(&S.d[0][0], &tm.d, c0, t0 - 1, bar);  // done[t-1]
-        }
-        if (++iss_chunk == n_chunks) { iss_chunk = 0; iss_strip += gridDim.x; }
-        if (++iss_stage == n_stages) iss_stage = 0;
-    };
-    // ---- store state (thread 0 only): the tile whose outputs sit in outs[par ^ 1] -----
-    bool st_pending = false;
-    int st_c0 = 0, st_t0 = 0;
-    auto store_tile = [&](int buf) {
-        if (REVERSE && st_t0 < 0) {
-            const int skip = -st_t0;  // rows of the staging tile that lie before t = 0
-            tma_store_2d(&tm.o0_rag, &outs[buf].o[0][skip][0], st_c0, 0);
-            tma_store_2d(&tm.o1_rag, &outs[buf].o[1][skip][0], st_c0, 0);
-            if (HAS_PRE) tma_store_2d(&tm.o2_rag, &outs[buf].o[PRE_SLOT][skip][0], st_c0, 0);
-        } else {
-            tma_store_2d(&tm.o0, &outs[buf].o[0][0][0], st_c0, st_t0);
-            if (REVERSE) tma_store_2d(&tm.o1, &outs[buf].o[1][0][0], st_c0, st_t0);
-            if (HAS_PRE) tma_store_2d(&tm.o2, &outs[buf].o[PRE_SLOT][0][0], st_c0, st_t0);
-        }
-        tma_store_commit();
-    };
-    if (threadIdx.x == 0) {
-        tma_prefetch_desc(&tm.r);
-        if (REVERSE) tma_prefetch_desc(&tm.v);
-        tma_prefetch_desc(&tm.d);
-        for (int s = 0; s < n_stages && iss_strip < n_strips; ++s) issue_one();
-        tma_prefetch_desc(&tm.o0);
-        if (REVERSE) tma_prefetch_desc(&tm.o1);
-        if (HAS_PRE) tma_prefetch_desc(&tm.o2);
-    }
-
-    const ACC gamma = (ACC)p.gamma;
-    const ACC gl = (ACC)(p.gamma * p.lambda);
-    double inv_denom = 1.0;
-    float clip_lo = 0.f, clip_hi = 0.f;
-    if (HAS_PRE) {
-        if (p.reward_var != nullptr) inv_denom = 1.0 / sqrt(*p.reward_var + p.reward_eps);
-        clip_lo = p.clip_lo;
-        clip_hi = p.clip_hi;
-    }
-
-    // fused statistics of out0 (HAS_STATS): per-thread sums of (y - K) and (y - K)^2 around a pivot K
-    // (the first value the thread produces); float32 inside a tile, float64 across tiles
-    float st_piv = 0.f;
-    bool st_has = false;
-    double st_s1 = 0.0, st_s2 = 0.0;
-    unsigned st_n = 0;
-
-    int stage = 0, par = 0;
-    uint32_t phase = 0;
-    const int i0 = warp * R;
-    for (int strip = blockIdx.x; strip < n_strips; strip += gridDim.x) {
-        const int64_t col = (int64_t)strip * W + lane;
-        const bool col_ok = col < p.B;
-        const bool strip_full = (int64_t)(strip + 1) * W <= p.B;
-        ACC carry0;  // scan value entering the first tile of the strip, per column
-        if (MODE == 0) carry0 = (ACC)0;
-        else if (MODE == 1) carry0 = col_ok ? (ACC)p.boot[col] : (ACC)0;
-        else carry0 = col_ok ? (ACC)p.prev_ret[col] : (ACC)0;
-        float halo_v = 0.f;  // GAE: value[t+1] for the last row of the first tile = bootstrap value
-        if (MODE == 0 && warp == NWARPS - 1) halo_v = col_ok ? p.boot[col] : 0.f;
-        bool first_prev_done = false;
-        if (MODE == 2 && warp == 0) first_prev_done = col_ok ? (p.prev_done[col] != 0) : false;
-
-        for (int k = 0; k < n_chunks; ++k) {
-            const int64_t t0 = REVERSE ? T - (int64_t)(k + 1) * TC : (int64_t)k * TC;
-            const StageT &S = stages[stage];
-            OutT &O = outs[par];
-            mbar_wait(&sh->full[stage], phase);
-
-            ACC A[R], C[R];
-            float vreg[R];
-            (void)vreg;
-
-            if (REVERSE) {
-                float vnext_f = 0.f;
-                if (MODE == 0) {
-                    if (warp == NWARPS - 1) vnext_f = (k == 0) ? halo_v : sh->halo[par ^ 1][lane];
-                    else vnext_f = S.v[i0 + R][lane];
-                }
-                ACC a = (ACC)0, c = (ACC)1;
-#pragma unroll
-                for (int u = R - 1; u >= 0; --u) {
-                    float rf = S.r[i0 + u][lane];
-                    const float vf = S.v[i0 + u][lane];
-                    const bool dn = S.d[i0 + u][lane] != 0;
-                    if (HAS_PRE) {
-                        rf = __double2float_rn((double)rf * inv_denom);
-                        rf = fminf(fmaxf(rf, clip_lo), clip_hi);
-                        O.o[PRE_SLOT][i0 + u][lane] = rf;
-                    }
-                    vreg[u] = vf;
-                    const ACC cc = dn ? (ACC)0 : (MODE == 0 ? gl : gamma);
-                    if (MODE == 0) {
-                        const ACC v = (ACC)vf;
-                        // done masks value[t+1] in float32 (one select) instead of masking gamma
-                        const ACC delta = fma(gamma, (ACC)(dn ? 0.f : vnext_f), (ACC)rf) - v;
-                        a = fma(cc, a, delta);
-                        vnext_f = vf;
-                    } else {
-                        a = fma(cc, a, (ACC)rf);
-                    }
-                    c = cc * c;
-                    A[u] = a;
-                    C[u] = c;
-                }
-                sh->aggA[par][warp][lane] = a;
-                sh->aggC[par][warp][lane] = c;
-                if (MODE == 0 && warp == 0) sh->halo[par][lane] = vreg[0];
-            } else {
-                // forward: x_t = r_t + g*~done[t-1]*x_{t-1}; S.d holds done rows t0-1 .. t0+TC-2
-                ACC a = (ACC)0, c = (ACC)1;
-#pragma unroll
-                for (int u = 0; u < R; ++u) {
-                    const float rf = S.r[i0 + u][lane];
-                    bool dn = S.d[i0 + u][lane] != 0;
-                    if (u == 0 && warp == 0 && k == 0) dn = first_prev_done;
-                    const ACC cc = dn ? (ACC)0 : gamma;
-                    a = fma(cc, a, (ACC)rf);
-                    c = cc * c;
-                    A[u] = a;
-                    C[u] = c;
-                }
-                sh->aggA[par][warp][lane] = a;
-                sh->aggC[par][warp][lane] = c;
-            }
-
-            // outs[par] was handed to the TMA one iteration back (tile k-2): it must have been read
-            if (threadIdx.x == 0) tma_store_wait_read<0>();
-            __syncthreads();  // stage fully read; aggregates visible; outs[par ^ 1] complete; outs[par] free
-
-            if (threadIdx.x == 0) {
-                if (iss_strip < n_strips) issue_one();   // refill the input stage just consumed
-                if (st_pending) store_tile(par ^ 1);     // previous tile's outputs -> global
-                st_pending = true;
-                st_c0 = strip * W;
-                st_t0 = (int)t0;
-            }
-
-            // Carry entering this warp's rows: the strip carry of the tile (published through smem by
-            // the warp that finished the previous tile's chain) composed with the aggregates of the
-            // warps that precede this one in scan order.  The last warp of the chain publishes the
-            // carry for the next tile.
-            ACC cin = (k == 0) ? carry0 : sh->carry[par ^ 1][lane];
-            if (REVERSE) {
-                for (int w = NWARPS - 1; w > warp; --w) cin = fma(sh->aggC[par][w][lane], cin, sh->aggA[par][w][lane]);
-                if (warp == 0) sh->carry[par][lane] = fma(C[0], cin, A[0]);
-            } else {
-                for (int w = 0; w < warp; ++w) cin = fma(sh->aggC[par][w][lane], cin, sh->aggA[par][w][lane]);
-                if (warp == NWARPS - 1) sh->carry[par][lane] = fma(C[R - 1], cin, A[R - 1]);
-            }
-
-            // pass 2: finalise from registers into the output staging tile
-            // (statistics: interior tiles without a mask take a predicate-free path)
-            const bool stats_fast = HAS_STATS && p.valid == nullptr && strip_full && t0 >= 0 && t0 + TC <= T;
-            const int u_lo = (int)((t0 + i0 < 0) ? -(t0 + i0) : 0);                  // first row of this warp inside [0, T)
-            const int u_hi = (int)((T - (t0 + i0) < R) ? (T - (t0 + i0)) : R);       // one past the last
-            const uint8_t *vp = (HAS_STATS && p.valid != nullptr) ? p.valid + (t0 + i0) * p.ld_valid + col : nullptr;
-            float s1 = 0.f, s2 = 0.f;  // float32 micro-accumulation of this tile's outputs
-            float ystat[HAS_STATS ? R : 1];
-            (void)ystat;
-#pragma unroll
-            for (int u = 0; u < R; ++u) {
-                const float x = to_f32(fma(C[u], cin, A[u]));
-                float y0;
-                if (MODE == 0) {
-                    y0 = x;
-                    O.o[0][i0 + u][lane] = x;
-                    O.o[1][i0 + u][lane] = __fadd_rn(x, vreg[u]);
-                } else if (MODE == 1) {
-                    y0 = __fsub_rn(x, vreg[u]);
-                    O.o[1][i0 + u][lane] = x;
-                    O.o[0][i0 + u][lane] = y0;
-                } else {
-                    y0 = x;
-                    O.o[0][i0 + u][lane] = x;
-                }
-                if (HAS_STATS) ystat[u] = y0;
-            }
-            if (HAS_STATS) {
-                if (!st_has) {  // pivot: any value of the data's magnitude will do (uniform within the warp)
-                    st_piv = __shfl_sync(0xffffffffu, ystat[0], 0);
-                    st_has = true;
-                }
-                if (stats_fast) {
-#pragma unroll
-                    for (int u = 0; u < R; ++u) {
-                        const float d = ystat[u] - st_piv;
-                        s1 += d;
-                        s2 = fmaf(d, d, s2);
-                    }
-                } else {
-#pragma unroll
-                    for (int u = 0; u < R; ++u) {
-                        const float d = ystat[u] - st_piv;
-                        bool ok = col_ok && u >= u_lo && u < u_hi;
-                        if (ok && vp != nullptr) ok = vp[(int64_t)u * p.ld_valid] != 0;
-                        if (ok) {
-                            s1 += d;
-                            s2 = fmaf(d, d, s2);
-                            ++st_n;
-                        }
-                    }
-                }
-            }
-            fence_proxy_async_smem();  // staging-tile writes -> visible to the TMA store issued after the next barrier
-            if (HAS_STATS) {
-                if (stats_fast) st_n += R;
-                st_s1 += (double)s1;
-                st_s2 += (double)s2;
-            }
-
-            par ^= 1;
-            if (++stage == n_stages) { stage = 0; phase ^= 1u; }
-        }
-    }
-
-    __syncthreads();
-    if (threadIdx.x == 0 && st_pending) store_tile(par ^ 1);  // last tile's outputs -> global (async)
-    if (HAS_STATS) {  // the grid reduction overlaps the drain of the last stores
-        Sums acc;
-        acc.n = (double)st_n; acc.s1 = st_s1; acc.s2 = st_s2; acc.piv = (double)st_piv;
-        moments_tail<true>(acc, p.tail, red_scratch);
-    }
-    // smem must stay alive (and the global writes complete) before the CTA retires
-    if (threadIdx.x == 0) tma_store_wait<0>();
-}
-
-
+//
 // ---------------------------------------------------------------------------------
-// Software-pipelined variant (default).  Same tiles, shared-memory layout and numerics as
-// scan_chunked_kernel, but the two register passes of consecutive tiles are fused: between two CTA
-// barriers every warp finalises tile j (independent FMAs + staging stores) while it scans tile j+1
+// Software-pipelined tile loop: the two register passes of consecutive tiles are fused -- between two
+// CTA barriers every warp finalises tile j (independent FMAs + staging stores) while it scans tile j+1
 // (the dependent chain), row by row in one unrolled loop, so the chain's latency hides behind the
 // independent work instead of being exposed twice per tile.  The aggregates of the warps are
 // fetched with independent shared-memory loads before the (predicated) compose chain.
 // ---------------------------------------------------------------------------------
-template <int MODE, typename ACC, int NW, int R, bool HAS_PRE, bool HAS_STATS>
+//
+// RESIDENT (reverse scans only) fuses NormalizeAdvantage (norm_advantage.py:30-56) into the same launch:
+// the un-normalised advantage of every tile is parked in TENSOR MEMORY (tcgen05.st, 16 columns per
+// warp and tile -- the 256 KB of TMEM are otherwise idle on this path) instead of being written out;
+// after the last tile every CTA publishes its partial moments to all CTAs of all ranks (gx_publish /
+// gx_collect: grid barrier and multi-GPU all-gather in one step), then reads its tiles back
+// (tcgen05.ld), normalises them in float32 and stores the advantage ONCE, each warp streaming its own
+// R-row slabs through the (now idle) input ring by TMA.  HBM traffic = the compulsory 17 B/transition.
+// The grid must be co-resident (cooperative launch, one CTA per SM).
+template <int MODE, typename ACC, int NW, int R, bool HAS_PRE, bool HAS_STATS, bool RESIDENT = false>
 __global__ void __launch_bounds__(NW * 32)
 scan_pipelined_kernel(const __grid_constant__ TensorMaps tm, const Params p)
 {
     constexpr int TC = NW * R;
     constexpr bool REVERSE = (MODE != 2);
+    static_assert(!RESIDENT || (REVERSE && HAS_STATS), "the resident variant is a reverse scan with statistics");
     constexpr int N_OUT = (REVERSE ? 2 : 1) + (HAS_PRE ? 1 : 0);
-    constexpr int PRE_SLOT = N_OUT - 1;
+    constexpr int N_STG = RESIDENT ? N_OUT - 1 : N_OUT;   // staging slots: out0 does not pass through smem when resident
+    constexpr int RET_SLOT = RESIDENT ? 0 : 1;
+    constexpr int PRE_SLOT = N_STG - 1;
     constexpr uint32_t TX_BYTES = REVERSE ? (sizeof(float) * TC * W * 2 + TC * W) : (sizeof(float) * TC * W + TC * W);
     using StageT = Stage<TC>;
-    using OutT = OutTile<TC, N_OUT>;
+    using OutT = OutTile<TC, N_STG>;
     using SharedT = Shared<ACC, NW>;
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -538,11 +287,25 @@ scan_pipelined_kernel(const __grid_constant__ TensorMaps tm, const Params p)
     const int n_stages = p.n_stages, n_chunks = p.n_chunks, n_strips = p.n_strips;
     const int64_t T = p.T;
 
+    __shared__ uint32_t s_tmem_base, s_epoch;
     if (threadIdx.x == 0) {
         for (int s = 0; s < n_stages; ++s) mbar_init(&sh->full[s], 1);
         fence_proxy_async_smem();
+        if (RESIDENT) s_epoch = gx_epoch(p.gx);
+    }
+    if (RESIDENT) {
+        if (warp == 0) {
+            __syncwarp();  // .sync.aligned: the whole warp, converged
+            tmem_alloc(&s_tmem_base, (uint32_t)p.tmem_cols);
+        }
+        tmem_fence_before_sync();
     }
     __syncthreads();
+    uint32_t tmem_warp = 0;  // this warp's lane quarter and column half of tile 0
+    if (RESIDENT) {
+        tmem_fence_after_sync();
+        tmem_warp = s_tmem_base + ((uint32_t)(warp & 3) << 21) + (uint32_t)((warp >> 2) * R);
+    }
 
     // ---- producer state (thread 0 only) -------------------------------------------------
     int iss_strip = blockIdx.x, iss_chunk = 0, iss_stage = 0;
@@ -568,12 +331,12 @@ scan_pipelined_kernel(const __grid_constant__ TensorMaps tm, const Params p)
     auto store_tile = [&](int buf) {
         if (REVERSE && st_t0 < 0) {
             const int skip = -st_t0;
-            tma_store_2d(&tm.o0_rag, &outs[buf].o[0][skip][0], st_c0, 0);
-            tma_store_2d(&tm.o1_rag, &outs[buf].o[1][skip][0], st_c0, 0);
+            if (!RESIDENT) tma_store_2d(&tm.o0_rag, &outs[buf].o[0][skip][0], st_c0, 0);
+            tma_store_2d(&tm.o1_rag, &outs[buf].o[RET_SLOT][skip][0], st_c0, 0);
             if (HAS_PRE) tma_store_2d(&tm.o2_rag, &outs[buf].o[PRE_SLOT][skip][0], st_c0, 0);
         } else {
-            tma_store_2d(&tm.o0, &outs[buf].o[0][0][0], st_c0, st_t0);
-            if (REVERSE) tma_store_2d(&tm.o1, &outs[buf].o[1][0][0], st_c0, st_t0);
+            if (!RESIDENT) tma_store_2d(&tm.o0, &outs[buf].o[0][0][0], st_c0, st_t0);
+            if (REVERSE) tma_store_2d(&tm.o1, &outs[buf].o[RET_SLOT][0][0], st_c0, st_t0);
             if (HAS_PRE) tma_store_2d(&tm.o2, &outs[buf].o[PRE_SLOT][0][0], st_c0, st_t0);
         }
         tma_store_commit();
@@ -583,7 +346,7 @@ scan_pipelined_kernel(const __grid_constant__ TensorMaps tm, const Params p)
         if (REVERSE) tma_prefetch_desc(&tm.v);
         tma_prefetch_desc(&tm.d);
         for (int s = 0; s < n_stages && iss_strip < n_strips; ++s) issue_one();
-        tma_prefetch_desc(&tm.o0);
+        if (!RESIDENT) tma_prefetch_desc(&tm.o0);
         if (REVERSE) tma_prefetch_desc(&tm.o1);
         if (HAS_PRE) tma_prefetch_desc(&tm.o2);
     }
@@ -617,6 +380,7 @@ scan_pipelined_kernel(const __grid_constant__ TensorMaps tm, const Params p)
     // cursor of the tile being scanned (pass 1) and of the tile being finalised (pass 2)
     int nx_strip = blockIdx.x, nx_k = 0;
     int cu_strip = 0, cu_k = 0;
+    int cu_idx = -1;  // index of the tile being finalised among this CTA's tiles (resident: its TMEM slot)
     ACC nx_carry0 = (ACC)0, cu_carry0 = (ACC)0;
     int stage = 0, par = 0;  // input stage and staging/aggregate parity of the tile being scanned
     uint32_t phase = 0;
@@ -699,6 +463,8 @@ scan_pipelined_kernel(const __grid_constant__ TensorMaps tm, const Params p)
             }
         }
         ACC a = (ACC)0, c = (ACC)1;
+        float xa[R];  // resident: this warp's R advantages of the tile, bound for TMEM (dead otherwise)
+        (void)xa;
         auto rows = [&](auto fast_tag) {
             constexpr bool FAST = decltype(fast_tag)::value;
             float ystat[(HAS_STATS && !FAST) ? R : 1];
@@ -712,16 +478,17 @@ scan_pipelined_kernel(const __grid_constant__ TensorMaps tm, const Params p)
                     float y0;
                     if (MODE == 0) {
                         y0 = x;
-                        O.o[0][i0 + u][lane] = x;
-                        O.o[1][i0 + u][lane] = __fadd_rn(x, vreg[u]);
+                        if (!RESIDENT) O.o[0][i0 + u][lane] = x;
+                        O.o[RET_SLOT][i0 + u][lane] = __fadd_rn(x, vreg[u]);
                     } else if (MODE == 1) {
                         y0 = __fsub_rn(x, vreg[u]);
-                        O.o[1][i0 + u][lane] = x;
-                        O.o[0][i0 + u][lane] = y0;
+                        O.o[RET_SLOT][i0 + u][lane] = x;
+                        if (!RESIDENT) O.o[0][i0 + u][lane] = y0;
                     } else {
                         y0 = x;
                         O.o[0][i0 + u][lane] = x;
                     }
+                    if (RESIDENT) xa[u] = y0;
                     if (HAS_PRE) O.o[PRE_SLOT][i0 + u][lane] = rpre[u];
                     if (HAS_STATS) {
                         if (FAST) {
@@ -792,6 +559,7 @@ scan_pipelined_kernel(const __grid_constant__ TensorMaps tm, const Params p)
         } else {
             rows(std::false_type{});
         }
+        if (P2 && RESIDENT) tmem_st<R>(tmem_warp + (uint32_t)(cu_idx * 2 * R), xa);
         if (P1) {
             sh->aggA[par][warp][lane] = a;
             sh->aggC[par][warp][lane] = c;
@@ -811,6 +579,7 @@ scan_pipelined_kernel(const __grid_constant__ TensorMaps tm, const Params p)
         // ---- advance the cursors ---------------------------------------------------------
         if (P1) {
             cu_strip = nx_strip; cu_k = nx_k; cu_carry0 = nx_carry0;
+            ++cu_idx;
             if (++nx_k == n_chunks) { nx_k = 0; nx_strip += gridDim.x; }
             par ^= 1;
             if (++stage == n_stages) { stage = 0; phase ^= 1u; }
@@ -826,7 +595,83 @@ scan_pipelined_kernel(const __grid_constant__ TensorMaps tm, const Params p)
     __syncthreads();
     // after the last body: the final tile sits in outs[par ^ 1]
     if (threadIdx.x == 0 && st_pending) store_tile(par ^ 1);
-    if (HAS_STATS && !(p.debug & 2)) {
+    if constexpr (RESIDENT) {
+        // ---- statistics of the whole batch: publish this CTA's moments, collect everybody's -------
+        __shared__ double s_pub[3];
+        __shared__ float s_mean, s_denom;
+        const uint32_t epoch = s_epoch;
+        Sums acc;
+        acc.n = (double)st_n; acc.s1 = st_s1; acc.s2 = st_s2; acc.piv = (double)st_piv;
+        const Sums blk = block_reduce_sums_warp_pivot(acc, red_scratch);
+        if (threadIdx.x == 0) {
+            const Moments m = to_moments(blk);
+            s_pub[0] = m.n; s_pub[1] = m.mean; s_pub[2] = m.m2;
+        }
+        __syncthreads();
+        gx_publish(p.gx, epoch, s_pub);
+        static_assert(sizeof(Moments) <= sizeof(Sums), "warp scratch is reused for Moments");
+        const Moments all = gx_collect(p.gx, epoch, reinterpret_cast<Moments *>(red_scratch));
+        if (threadIdx.x == 0) {
+            s_mean = __double2float_rn(all.mean);
+            s_denom = __fadd_rn(__double2float_rn(sqrt(all.m2 / all.n)), p.adv_eps);
+            if (blockIdx.x == 0) {
+                p.adv_moments_out[0] = all.n; p.adv_moments_out[1] = all.mean; p.adv_moments_out[2] = all.m2;
+            }
+            gx_retire(p.gx, epoch);
+        }
+        __syncthreads();
+        const float mean = s_mean, denom = s_denom;
+        // ---- advantage = (adv - mean) / (std + eps), float32 (norm_advantage.py:51-54), stored once --
+        tmem_wait_st();
+        // the input ring is idle now (every requested tile has been consumed): its first bytes become
+        // per-warp staging slabs for the TMA stores, `n_out_bufs` tiles deep
+        float *slabs = reinterpret_cast<float *>(smem_raw);
+        const int n_bufs = p.n_out_bufs;
+        int n_tma = 0;  // slabs this warp has handed to the TMA so far
+        for (int j = 0; j < n_tiles; ++j) {
+            const int strip = (int)blockIdx.x + (j / n_chunks) * (int)gridDim.x;
+            const int k = j - (j / n_chunks) * n_chunks;
+            const int64_t row0 = T - (int64_t)(k + 1) * TC + i0;  // first row of this warp's slab
+            float x[R];
+            tmem_ld<R>(tmem_warp + (uint32_t)(j * 2 * R), x);
+#pragma unroll
+            for (int u = 0; u < R; ++u) x[u] = __fdiv_rn(__fsub_rn(x[u], mean), denom);
+            if (row0 >= 0 && !(p.debug & 4)) {
+                float *slab = slabs + ((size_t)(n_tma % n_bufs) * TC + i0) * W;
+                if (n_tma >= n_bufs) {  // the slab was handed to the TMA n_bufs stores ago: it must have been read
+                    if (lane == 0) {
+                        if (n_bufs == 4) tma_store_wait_read<3>();
+                        else tma_store_wait_read<1>();
+                    }
+                    __syncwarp();
+                }
+#pragma unroll
+                for (int u = 0; u < R; ++u) slab[u * W + lane] = x[u];
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_2d(&tm.o0_warp, slab, strip * W, (int)row0);
+                    tma_store_commit();
+                }
+                ++n_tma;
+            } else {
+                // ragged first rows of the batch (or the experiment switch): plain coalesced stores
+                const int64_t col = (int64_t)strip * W + lane;
+                if (col < p.B) {
+#pragma unroll
+                    for (int u = 0; u < R; ++u)
+                        if (row0 + u >= 0) p.out0_raw[(row0 + u) * p.ld_out0_raw + col] = x[u];
+                }
+            }
+        }
+        if (lane == 0) tma_store_wait<0>();  // shared memory must outlive the bulk reads
+        tmem_fence_before_sync();
+        __syncthreads();
+        if (warp == 0) {
+            __syncwarp();
+            tmem_dealloc(s_tmem_base, (uint32_t)p.tmem_cols);
+        }
+    } else if (HAS_STATS && !(p.debug & 2)) {
         Sums acc;
         acc.n = (double)st_n; acc.s1 = st_s1; acc.s2 = st_s2; acc.piv = (double)st_piv;
         moments_tail<true>(acc, p.tail, red_scratch);
@@ -908,12 +753,11 @@ bool scan_chunked_supported(const float *reward, int64_t ld_r, const float *valu
     return tma_ok_u8(done, ld_d);
 }
 
-// tile geometry: 0 = auto, 1 = 8 warps x 8 rows (64-row tiles), 2 = 8 warps x 16 rows, 3 = 16 warps x 8 rows
+// tile geometry: 0 = auto, 1 = 8 warps x 8 rows (64-row tiles), 2 = 8 warps x 16 rows (128-row tiles)
 static int g_chunked_geom = 0;
-static int g_chunked_f32 = 0;        // 1: float32 affine maps (fast variant)
 static int g_scan_debug = 0;
 static int g_scan_max_stages = 0;     // experiments: cap on the input ring depth (plb_set_tuning key 9)
-static int g_chunked_pipe = 1;       // 1: software-pipelined tile loop (default), 0: two-phase tile loop
+static int g_resident = 1;            // 0: never take the resident (TMEM) variant (plb_set_tuning key 12)
 
 template <int MODE, typename ACC, int NW, int R, bool HAS_PRE, bool HAS_STATS>
 static int launch_chunked_inst(const chunked::TensorMaps &tm, chunked::Params p, int sms, cudaStream_t stream)
@@ -930,10 +774,8 @@ static int launch_chunked_inst(const chunked::TensorMaps &tm, chunked::Params p,
     // 228 KB of shared memory per SM, 1 KB reserved per CTA, ~1 KB of static scratch per CTA.
     int ctas_per_sm = p.n_strips <= sms ? 1 : (p.n_strips <= 2 * sms ? 2 : 3);
     if (NW > 8) ctas_per_sm = 1;
-    auto kern = g_chunked_pipe ? scan_pipelined_kernel<MODE, ACC, NW, R, HAS_PRE, HAS_STATS>
-                               : scan_chunked_kernel<MODE, ACC, NW, R, HAS_PRE, HAS_STATS>;
-    static thread_local size_t static_smem_v[2] = {~(size_t)0, ~(size_t)0};
-    size_t &static_smem = static_smem_v[g_chunked_pipe ? 1 : 0];
+    auto kern = scan_pipelined_kernel<MODE, ACC, NW, R, HAS_PRE, HAS_STATS>;
+    static thread_local size_t static_smem = ~(size_t)0;
     if (static_smem == ~(size_t)0) {
         cudaFuncAttributes attr;
         PLB_CUDA(cudaFuncGetAttributes(&attr, kern));
@@ -954,8 +796,7 @@ static int launch_chunked_inst(const chunked::TensorMaps &tm, chunked::Params p,
     p.n_stages = stages;
     const size_t smem = stage_bytes * stages + fixed_bytes;
     const int grid = p.n_strips < sms * ctas_per_sm ? p.n_strips : sms * ctas_per_sm;
-    static thread_local bool configured_v[2] = {false, false};
-    bool &configured = configured_v[g_chunked_pipe ? 1 : 0];
+    static thread_local bool configured = false;
     if (!configured) {
         PLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
         configured = true;
@@ -965,6 +806,78 @@ static int launch_chunked_inst(const chunked::TensorMaps &tm, chunked::Params p,
     return PLB_OK;
 }
 
+// Geometry of the resident variant: one persistent CTA per SM, every CTA's advantage tiles parked in
+// its SM's tensor memory (512 columns = 16 tiles of 128 rows x 32 columns, or 32 tiles of 64 rows).
+struct ResidentGeometry {
+    int R;          // rows per warp: 16 (128-row tiles) or 8 (64-row tiles, T <= 64)
+    int grid, n_chunks, tiles_per_cta, tmem_cols;
+};
+static bool resident_geometry(int64_t T, int64_t B, int sms, ResidentGeometry *g)
+{
+    using namespace chunked;
+    if (sms <= 0 || sms > GX_MAX_SLOTS) return false;
+    const int64_t strips = ceil_div(B, W);
+    g->R = T <= 64 ? 8 : 16;
+    const int TC = 8 * g->R;
+    g->grid = (int)(strips < sms ? strips : sms);
+    const int64_t chunks = ceil_div(T, TC);
+    const int64_t tiles = ceil_div(strips, g->grid) * chunks;
+    const int64_t cols = tiles * 2 * g->R;
+    if (cols > 512) return false;
+    g->n_chunks = (int)chunks;
+    g->tiles_per_cta = (int)tiles;
+    int c = 32;
+    while (c < cols) c <<= 1;
+    g->tmem_cols = c;
+    return true;
+}
+
+template <int MODE, int R, bool HAS_PRE>
+static int launch_resident_inst(const chunked::TensorMaps &tm, chunked::Params p, const ResidentGeometry &geo,
+                                cudaStream_t stream)
+{
+    using namespace chunked;
+    constexpr int NW = 8, TC = NW * R;
+    constexpr int N_STG = 1 + (HAS_PRE ? 1 : 0);
+    auto kern = scan_pipelined_kernel<MODE, double, NW, R, HAS_PRE, true, true>;
+    const size_t stage_bytes = sizeof(Stage<TC>);
+    const size_t fixed_bytes = sizeof(Shared<double, NW>) + 2 * sizeof(OutTile<TC, N_STG>);
+    static thread_local size_t static_smem = ~(size_t)0;
+    if (static_smem == ~(size_t)0) {
+        cudaFuncAttributes attr;
+        PLB_CUDA(cudaFuncGetAttributes(&attr, kern));
+        static_smem = attr.sharedSizeBytes;
+        PLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024 - static_smem)));
+    }
+    const size_t smem_cap = 227 * 1024 - static_smem;
+    int stages = (int)((smem_cap - fixed_bytes) / stage_bytes);
+    if (stages > MAX_STAGES) stages = MAX_STAGES;
+    if (g_scan_max_stages > 0 && stages > g_scan_max_stages) stages = g_scan_max_stages;
+    // (no cap at the number of chunks: the final store phase reuses the ring as staging slabs)
+    PLB_REQUIRE(stages >= 1, PLB_ERR_UNSUPPORTED, "resident scan does not fit in shared memory");
+    p.n_stages = stages;
+    p.n_strips = (int)ceil_div(p.B, W);
+    p.n_chunks = geo.n_chunks;
+    p.debug = g_scan_debug;
+    p.tmem_cols = geo.tmem_cols;
+    const size_t tile_bytes = (size_t)TC * W * sizeof(float);
+    p.n_out_bufs = (stage_bytes * stages >= 4 * tile_bytes) ? 4 : 2;
+    PLB_REQUIRE(stage_bytes * stages >= 2 * tile_bytes, PLB_ERR_UNSUPPORTED, "resident scan: ring too small for the store phase");
+    const size_t smem = stage_bytes * stages + fixed_bytes;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)geo.grid);
+    cfg.blockDim = dim3(NW * 32);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;  // every CTA waits for every other: the grid must be co-resident
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    PLB_CUDA(cudaLaunchKernelEx(&cfg, kern, tm, p));
+    count_launch(1);
+    return PLB_OK;
+}
 
 struct ChunkedIO {
     const float *reward; int64_t ld_r;
@@ -975,25 +888,13 @@ struct ChunkedIO {
     float *reward_out; int64_t ld_ro;
 };
 
+// tensor maps of one scan launch with TC-row tiles (warp_rows > 0: also out0 with a warp-slab box)
 template <int MODE>
-static int launch_chunked(const ChunkedIO &io, chunked::Params p, bool has_pre, cudaStream_t stream)
+static int build_tensor_maps(const ChunkedIO &io, const chunked::Params &p, bool has_pre, int TC, int warp_rows,
+                             chunked::TensorMaps *out)
 {
     using namespace chunked;
-    const int sms = sm_count();
-    PLB_REQUIRE(sms > 0, PLB_ERR_UNSUPPORTED, "no CUDA device");
-    // one CTA per SM (few strips): 8 warps x 16 rows = 128-row tiles (measured fastest at C1: 13.8 us
-    // vs 15.2 us for 16 warps x 8 rows and 18.3 us for 64-row tiles); several CTAs per SM (many
-    // strips): 8 warps x 8 rows = 64-row tiles.
-    int geom = g_chunked_geom;
-    if (geom == 0) {
-        // few strips (<= one per SM) or many long strips (>= 4 per SM, T >= 256): one persistent CTA per SM
-        // with 128-row tiles (C4: 49.8 us vs 55.0 us for 64-row tiles); in between: several CTAs per SM
-        const int64_t strips = ceil_div(p.B, W);
-        geom = (strips <= sms || (strips >= 4 * (int64_t)sms && p.T >= 256)) ? 2 : 1;
-    }
-    if (p.T <= 64) geom = 1;
-    const int TC = geom == 1 ? 64 : 128;
-    TensorMaps tm;
+    TensorMaps &tm = *out;
     int rc = make_tensor_map_2d(&tm.r, io.reward, 4, p.T, p.B, io.ld_r, TC, W);
     if (rc) return rc;
     if (MODE != 2) {
@@ -1030,6 +931,35 @@ static int launch_chunked(const ChunkedIO &io, chunked::Params p, bool has_pre, 
             if (rc) return rc;
         }
     }
+    tm.o0_warp = tm.o0;
+    if (warp_rows > 0) {
+        rc = make_tensor_map_2d(&tm.o0_warp, io.out0, 4, p.T, p.B, io.ld0, warp_rows, W);
+        if (rc) return rc;
+    }
+    return PLB_OK;
+}
+
+template <int MODE>
+static int launch_chunked(const ChunkedIO &io, chunked::Params p, bool has_pre, cudaStream_t stream)
+{
+    using namespace chunked;
+    const int sms = sm_count();
+    PLB_REQUIRE(sms > 0, PLB_ERR_UNSUPPORTED, "no CUDA device");
+    // one CTA per SM (few strips): 8 warps x 16 rows = 128-row tiles (measured fastest at C1: 13.8 us
+    // vs 15.2 us for 16 warps x 8 rows and 18.3 us for 64-row tiles); several CTAs per SM (many
+    // strips): 8 warps x 8 rows = 64-row tiles.
+    int geom = g_chunked_geom;
+    if (geom == 0) {
+        // few strips (<= one per SM) or many long strips (>= 4 per SM, T >= 256): one persistent CTA per SM
+        // with 128-row tiles (C4: 49.8 us vs 55.0 us for 64-row tiles); in between: several CTAs per SM
+        const int64_t strips = ceil_div(p.B, W);
+        geom = (strips <= sms || (strips >= 4 * (int64_t)sms && p.T >= 256)) ? 2 : 1;
+    }
+    if (p.T <= 64) geom = 1;
+    const int TC = geom == 1 ? 64 : 128;
+    TensorMaps tm;
+    const int rc = build_tensor_maps<MODE>(io, p, has_pre, TC, 0, &tm);
+    if (rc) return rc;
     const bool stats = p.tail.moments_out != nullptr;
 #define PLB_DISPATCH(ACC_, NW_, R_)                                                                          \
     do {                                                                                                     \
@@ -1040,15 +970,46 @@ static int launch_chunked(const ChunkedIO &io, chunked::Params p, bool has_pre, 
         if (stats) return launch_chunked_inst<MODE, ACC_, NW_, R_, false, true>(tm, p, sms, stream);         \
         return launch_chunked_inst<MODE, ACC_, NW_, R_, false, false>(tm, p, sms, stream);                   \
     } while (0)
-    if (g_chunked_f32) {
-        if (geom == 1) PLB_DISPATCH(float, 8, 8);
-        if (geom == 2) PLB_DISPATCH(float, 8, 16);
-        PLB_DISPATCH(float, 16, 8);
-    }
     if (geom == 1) PLB_DISPATCH(double, 8, 8);
-    if (geom == 2) PLB_DISPATCH(double, 8, 16);
-    PLB_DISPATCH(double, 16, 8);
+    PLB_DISPATCH(double, 8, 16);
 #undef PLB_DISPATCH
+}
+
+// reverse scan + NormalizeAdvantage in one cooperative launch (MODE 0 / 1)
+template <int MODE>
+static int launch_resident(const ChunkedIO &io, chunked::Params p, bool has_pre, cudaStream_t stream)
+{
+    using namespace chunked;
+    const int sms = sm_count();
+    PLB_REQUIRE(sms > 0, PLB_ERR_UNSUPPORTED, "no CUDA device");
+    ResidentGeometry geo;
+    PLB_REQUIRE(resident_geometry(p.T, p.B, sms, &geo), PLB_ERR_UNSUPPORTED,
+                "resident scan: the advantage of this batch does not fit in tensor memory");
+    PLB_REQUIRE(p.gx.peers != nullptr && p.gx.world >= 1 && p.gx.world <= GX_MAX_WORLD && p.gx.rank >= 0 &&
+                    p.gx.rank < p.gx.world && p.gx.slots >= geo.grid && p.gx.slots <= GX_MAX_SLOTS,
+                PLB_ERR_INVALID_ARGUMENT, "resident scan: bad grid-exchange description (world %d, slots %d, grid %d)",
+                p.gx.world, p.gx.slots, geo.grid);
+    TensorMaps tm;
+    const int rc = build_tensor_maps<MODE>(io, p, has_pre, 8 * geo.R, geo.R, &tm);
+    if (rc) return rc;
+    p.out0_raw = io.out0; p.ld_out0_raw = io.ld0;
+    if (geo.R == 16) {
+        if (has_pre) return launch_resident_inst<MODE, 16, true>(tm, p, geo, stream);
+        return launch_resident_inst<MODE, 16, false>(tm, p, geo, stream);
+    }
+    if (has_pre) return launch_resident_inst<MODE, 8, true>(tm, p, geo, stream);
+    return launch_resident_inst<MODE, 8, false>(tm, p, geo, stream);
+}
+
+bool resident_supported(const float *reward, int64_t ld_r, const float *value, int64_t ld_v, const uint8_t *done,
+                        int64_t ld_d, const float *adv, int64_t ld_a, const float *ret, int64_t ld_t,
+                        int64_t T, int64_t B)
+{
+    if (!g_resident || T <= 0 || B <= 0) return false;
+    if (!scan_chunked_supported(reward, ld_r, value, ld_v, done, ld_d, T, B, 1)) return false;
+    if (!tma_ok_f32(adv, ld_a) || !tma_ok_f32(ret, ld_t)) return false;
+    ResidentGeometry geo;
+    return resident_geometry(T, B, sm_count(), &geo);
 }
 
 int scan_reverse(int mode, const float *reward, int64_t ld_r, const float *value, int64_t ld_v,
@@ -1094,6 +1055,15 @@ int scan_reverse(int mode, const float *reward, int64_t ld_r, const float *value
             }
             p.valid = fusion->valid; p.ld_valid = fusion->ld_valid;
             p.tail = fusion->tail;
+            if (fusion->resident) {
+                PLB_REQUIRE(resident_supported(reward, ld_r, value, ld_v, done, ld_d, adv, ld_a, ret, ld_t, T, B),
+                            PLB_ERR_UNSUPPORTED, "resident scan not available for this shape");
+                PLB_REQUIRE(fusion->adv_moments_out != nullptr, PLB_ERR_INVALID_ARGUMENT, "adv_moments_out is null");
+                p.gx = fusion->gx;
+                p.adv_eps = (float)fusion->adv_eps;
+                p.adv_moments_out = fusion->adv_moments_out;
+                return mode == 0 ? launch_resident<0>(io, p, has_pre, stream) : launch_resident<1>(io, p, has_pre, stream);
+            }
         }
         return mode == 0 ? launch_chunked<0>(io, p, has_pre, stream) : launch_chunked<1>(io, p, has_pre, stream);
     }
@@ -1149,7 +1119,7 @@ int scan_forward(const float *reward, int64_t ld_r, const uint8_t *done, int64_t
         if (fusion != nullptr) {
             p.valid = fusion->valid; p.ld_valid = fusion->ld_valid;
             p.tail = fusion->tail;
-            if (fusion->carry_ret_out != nullptr && fusion->carry_done_out != nullptr && g_chunked_pipe != 0) {
+            if (fusion->carry_ret_out != nullptr && fusion->carry_done_out != nullptr) {
                 p.carry_ret_out = fusion->carry_ret_out; p.carry_done_out = fusion->carry_done_out;
                 p.done_raw = done; p.ld_done_raw = ld_d;
                 carry_in_kernel = true;
@@ -1177,8 +1147,7 @@ int plb_set_tuning(int key, int value)
 {
     switch (key) {
         case 0: plb::g_chunked_geom = value; return PLB_OK;
-        case 1: plb::g_chunked_f32 = value; return PLB_OK;
-        case 4: plb::g_chunked_pipe = value; return PLB_OK;
+        case 12: plb::g_resident = value; return PLB_OK;
         case 5: plb::g_scan_debug = value; return PLB_OK;
         case 9: plb::g_scan_max_stages = value; return PLB_OK;
         case 11: plb::set_normadv_ctas_per_sm(value); return PLB_OK;

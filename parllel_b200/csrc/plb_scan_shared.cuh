@@ -52,6 +52,28 @@ static inline MomentsTail make_tail(double *moments_out, void *workspace)
     return t;
 }
 
+// Grid-wide + cross-GPU statistics exchange of the resident advantage kernel (one protocol for both):
+// every CTA of every rank stores its partial (count, mean, M2) as an epoch-tagged record straight into
+// EVERY rank's buffer (its own included; NVLink P2P stores for the peers), then polls its own rank's
+// buffer until all world x slots records of the launch epoch have landed and merges them in a fixed
+// order -- so the grid barrier of one GPU and the all-gather across GPUs are the same step, with no
+// atomics, no last-CTA reduction and no second kernel.  Buffer layout (plb_grid_exchange_bytes):
+//     uint32 epoch @0 | uint32 exit_ticket @4 | uint32 status @8 (0 ok, 1 timed out)
+//     records @256: [2 (epoch parity)][world][slots] x 48 B = 3 x {lo, epoch, hi, epoch} 16-byte units
+struct GridXch {
+    unsigned char *const *peers;  // device array [world]: every rank's buffer (world == 1: just ours)
+    int rank, world;
+    int slots;                    // records per rank and epoch (>= the largest grid of any rank)
+};
+constexpr size_t GX_HEADER_BYTES = 256;
+constexpr size_t GX_RECORD_BYTES = 48;
+constexpr int GX_MAX_WORLD = 32;
+constexpr int GX_MAX_SLOTS = 1024;
+__host__ __device__ __forceinline__ size_t gx_total_bytes(int world, int slots)
+{
+    return GX_HEADER_BYTES + 2 * (size_t)world * (size_t)slots * GX_RECORD_BYTES;
+}
+
 // Optional work fused into the chunked scans (host-side description).
 struct ScanFusion {
     int has_pre;               // apply reward scale/clip on the load path
@@ -65,7 +87,18 @@ struct ScanFusion {
     MomentsTail tail;          // fused moments of advantage / past_return
     float *carry_ret_out;      // forward scan: receives out[T-1] per column (may alias prev_ret), or nullptr
     uint8_t *carry_done_out;   // forward scan: receives done[T-1] per column (may alias prev_done), or nullptr
+    // reverse scans, optional: NormalizeAdvantage fused into the same launch (resident kernel): the
+    // advantage stays on chip (TMEM) until the statistics of the whole (multi-GPU) batch are known
+    int resident;              // 1: requested; scan_reverse returns PLB_ERR_UNSUPPORTED if the shape cannot
+    GridXch gx;
+    double adv_eps;
+    double *adv_moments_out;   // [3] merged (count, mean, M2)
 };
+bool scan_chunked_supported(const float *reward, int64_t ld_r, const float *value, int64_t ld_v,
+                            const uint8_t *done, int64_t ld_d, int64_t T, int64_t B, int64_t inner);
+bool resident_supported(const float *reward, int64_t ld_r, const float *value, int64_t ld_v, const uint8_t *done,
+                        int64_t ld_d, const float *adv, int64_t ld_a, const float *ret, int64_t ld_t,
+                        int64_t T, int64_t B);
 
 int scan_reverse(int mode, const float *reward, int64_t ld_r, const float *value, int64_t ld_v,
                  const uint8_t *done, int64_t ld_d, const float *boot,
@@ -303,6 +336,195 @@ __device__ __forceinline__ Moments xch_wait_merge3(const XchRef &x)
         acc = merge(acc, m);
     }
     return acc;
+}
+
+// ---------------------------------------------------------------------------------
+// Tensor memory (TMEM) as an on-chip parking area: 128 lanes x 512 columns x 32 bit per SM.
+// Warp w may touch lanes [32*(w%4), 32*(w%4)+32); with the 32x32b shape thread i of the warp owns
+// lane base+i and register k goes to column base+k.  SASS: STTM / LDTM.
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t *smem_dst, uint32_t cols)  // one full warp; cols = 2^k in [32, 512]
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols)  // the allocating warp
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tmem_fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+template <int N>
+__device__ __forceinline__ void tmem_st(uint32_t taddr, const float (&x)[N])
+{
+    static_assert(N == 8 || N == 16, "tmem_st: 8 or 16 columns");
+    if constexpr (N == 16) {
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+                     ::"r"(taddr), "f"(x[0]), "f"(x[1]), "f"(x[2]), "f"(x[3]), "f"(x[4]), "f"(x[5]), "f"(x[6]), "f"(x[7]),
+                       "f"(x[8]), "f"(x[9]), "f"(x[10]), "f"(x[11]), "f"(x[12]), "f"(x[13]), "f"(x[14]), "f"(x[15])
+                     : "memory");
+    } else {
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                     ::"r"(taddr), "f"(x[0]), "f"(x[1]), "f"(x[2]), "f"(x[3]), "f"(x[4]), "f"(x[5]), "f"(x[6]), "f"(x[7])
+                     : "memory");
+    }
+}
+template <int N>
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, float (&x)[N])
+{
+    static_assert(N == 8 || N == 16, "tmem_ld: 8 or 16 columns");
+    if constexpr (N == 16) {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                     : "=f"(x[0]), "=f"(x[1]), "=f"(x[2]), "=f"(x[3]), "=f"(x[4]), "=f"(x[5]), "=f"(x[6]), "=f"(x[7]),
+                       "=f"(x[8]), "=f"(x[9]), "=f"(x[10]), "=f"(x[11]), "=f"(x[12]), "=f"(x[13]), "=f"(x[14]), "=f"(x[15])
+                     : "r"(taddr)
+                     : "memory");
+    } else {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                     : "=f"(x[0]), "=f"(x[1]), "=f"(x[2]), "=f"(x[3]), "=f"(x[4]), "=f"(x[5]), "=f"(x[6]), "=f"(x[7])
+                     : "r"(taddr)
+                     : "memory");
+    }
+    tmem_wait_ld();
+}
+
+// ---------------------------------------------------------------------------------
+// Grid exchange (see GridXch above).  gx_epoch / gx_publish / gx_collect / gx_retire are called by
+// every CTA of the launch, in that order; all ranks must issue the same sequence of launches on one
+// buffer set (a collective), because the epoch tag is each rank's own launch counter.
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t gx_epoch(const GridXch &g)  // any thread; the epoch of THIS launch
+{
+    return *reinterpret_cast<const volatile uint32_t *>(g.peers[g.rank]) + 1u;
+}
+
+__device__ __forceinline__ unsigned char *gx_record(unsigned char *buf, const GridXch &g, uint32_t epoch, int src_rank, int slot)
+{
+    return buf + GX_HEADER_BYTES + (((size_t)(epoch & 1u) * g.world + src_rank) * g.slots + slot) * GX_RECORD_BYTES;
+}
+
+// Publish this CTA's moments (read from `mine`, e.g. shared memory, by every participating thread) into
+// slot blockIdx.x of every rank, and empty records into the slots no CTA of this grid owns
+// (blockIdx.x + k * gridDim.x < slots).  Call with all threads of the CTA.
+__device__ __forceinline__ void gx_publish(const GridXch &g, uint32_t epoch, const double *mine)
+{
+    const int extra = (g.slots - 1 - (int)blockIdx.x) / (int)gridDim.x + 1;  // slots this CTA fills
+    for (int i = threadIdx.x; i < extra * g.world; i += blockDim.x) {
+        const int k = i / g.world, r = i - k * g.world;
+        const int slot = (int)blockIdx.x + k * (int)gridDim.x;
+        unsigned char *dst = gx_record(g.peers[r], g, epoch, g.rank, slot);
+#pragma unroll
+        for (int v = 0; v < 3; ++v) {
+            const unsigned long long bits = (k == 0) ? (unsigned long long)__double_as_longlong(mine[v]) : 0ull;
+            asm volatile("st.relaxed.sys.global.v4.u32 [%0], {%1, %2, %3, %4};"
+                         ::"l"(dst + 16 * v), "r"((uint32_t)bits), "r"(epoch), "r"((uint32_t)(bits >> 32)), "r"(epoch)
+                         : "memory");
+        }
+    }
+}
+
+// Wait for all world x slots records of `epoch` in this rank's buffer and merge them.  Records are
+// dealt to threads round-robin; each thread keeps up to four polls in flight (one L2 round trip per
+// batch), merges its records in index order, then lanes and warps merge in index order: the same
+// operations on the same data in every CTA of every rank, so all of them derive identical bits.
+// Returns the merged moments in thread 0 (other threads: partial).  `warp_scratch` >= 32 Moments.
+__device__ __forceinline__ Moments gx_collect(const GridXch &g, uint32_t epoch, Moments *warp_scratch)
+{
+    unsigned char *mine = g.peers[g.rank];
+    const int n_rec = g.world * g.slots;
+    Moments acc;
+    acc.n = 0.0; acc.mean = 0.0; acc.m2 = 0.0;
+    const long long t_start = clock64();
+    bool timed_out = false;
+    for (int base = threadIdx.x; base < n_rec; base += 4 * blockDim.x) {
+        double v[4][3];
+        unsigned pending = 0u;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (base + j * (int)blockDim.x < n_rec) pending |= 1u << j;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) v[j][c] = 0.0;
+        }
+        while (pending != 0u) {
+            uint4 q[4][3];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (pending & (1u << j)) {
+                    const int idx = base + j * (int)blockDim.x;  // = src_rank * slots + slot
+                    const unsigned char *src = mine + GX_HEADER_BYTES + ((size_t)(epoch & 1u) * n_rec + idx) * GX_RECORD_BYTES;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c)
+                        asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                                     : "=r"(q[j][c].x), "=r"(q[j][c].y), "=r"(q[j][c].z), "=r"(q[j][c].w)
+                                     : "l"(src + 16 * c)
+                                     : "memory");
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (pending & (1u << j)) {
+                    bool ok = true;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) ok = ok && q[j][c].y == epoch && q[j][c].w == epoch;
+                    if (ok) {
+#pragma unroll
+                        for (int c = 0; c < 3; ++c)
+                            v[j][c] = __longlong_as_double((long long)(((unsigned long long)q[j][c].z << 32) | (unsigned long long)q[j][c].x));
+                        pending &= ~(1u << j);
+                    }
+                }
+            }
+            if (pending != 0u && clock64() - t_start > 20000000000LL) {  // ~10 s: a peer never arrived
+                timed_out = true;
+                break;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            Moments m;
+            m.n = v[j][0]; m.mean = v[j][1]; m.m2 = v[j][2];
+            acc = merge(acc, m);
+        }
+        if (timed_out) break;
+    }
+    if (timed_out) {  // no trap: flag it for plb_grid_exchange_status() and poison the result
+        reinterpret_cast<volatile uint32_t *>(mine)[2] = 1u;
+        acc.mean = __longlong_as_double(0x7ff8000000000000LL);
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {  // lane l absorbs lane l + d: ascending index order
+        Moments o;
+        o.n = __shfl_down_sync(0xffffffffu, acc.n, d);
+        o.mean = __shfl_down_sync(0xffffffffu, acc.mean, d);
+        o.m2 = __shfl_down_sync(0xffffffffu, acc.m2, d);
+        if (lane + d < 32) acc = merge(acc, o);
+    }
+    if (lane == 0) warp_scratch[warp] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        acc = warp_scratch[0];
+        for (int w = 1; w < nwarps; ++w) acc = merge(acc, warp_scratch[w]);
+    }
+    return acc;
+}
+
+// Last CTA out advances the epoch for the next launch (off the critical path).  One thread per CTA,
+// after that CTA's gx_collect.
+__device__ __forceinline__ void gx_retire(const GridXch &g, uint32_t epoch)
+{
+    uint32_t *hdr = reinterpret_cast<uint32_t *>(g.peers[g.rank]);
+    __threadfence();
+    const uint32_t t = atomicAdd(hdr + 1, 1u);
+    if (t == gridDim.x - 1) {
+        hdr[1] = 0u;
+        __threadfence();
+        *reinterpret_cast<volatile uint32_t *>(hdr) = epoch;
+    }
 }
 
 // running_mean_std.py:23-30 for one feature: (mean, var) <- Chan merge with batch moments

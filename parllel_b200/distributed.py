@@ -71,6 +71,54 @@ class PeerExchange:
         _lib.check(rc, "plb_exchange_moments_p2p")
 
 
+class GridExchange:
+    """Buffers of the resident advantage kernel's in-kernel exchange (csrc/plb_scan_shared.cuh, GridXch):
+    every CTA of every rank stores its partial moments into every rank's buffer and collects all of them
+    from its own -- grid barrier and all-gather in one step.  With ``group`` None (one GPU) the buffer is
+    ordinary device memory; otherwise it is symmetric memory mapped into all peers (plumbing from
+    ``torch.distributed._symmetric_memory``), and creating it is a collective.  ``ok`` is False when
+    peer mapping is unavailable (the caller then keeps to the other routes)."""
+
+    def __init__(self, group=None, device=None) -> None:
+        lib = _lib.load()
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.slots = int(lib.plb_grid_exchange_slots())
+        self.ok = self.slots > 0
+        self.handle = None
+        single = group is None and not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1)
+        if single:
+            self.group, self.world, self.rank = None, 1, 0
+            self.buffer = torch.zeros(lib.plb_grid_exchange_bytes(1, max(self.slots, 1)), dtype=torch.uint8, device=self.device)
+            self.peer_table = torch.tensor([self.buffer.data_ptr()], dtype=torch.int64, device=self.device)
+            return
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            nbytes = lib.plb_grid_exchange_bytes(self.world, max(self.slots, 1))
+            if nbytes == 0:
+                raise RuntimeError(f"unsupported world size {self.world}")
+            self.buffer = symm_mem.empty(nbytes, dtype=torch.uint8, device=self.device)
+            self.buffer.zero_()
+            self.handle = symm_mem.rendezvous(self.buffer, self.group)
+            self.peer_table = torch.tensor([int(p) for p in self.handle.buffer_ptrs], dtype=torch.int64, device=self.device)
+            torch.cuda.synchronize(self.device)
+            good = 1
+        except Exception as err:  # no peer mapping on this system
+            import warnings
+            warnings.warn(f"grid exchange buffers unavailable ({err!r}); using the two-kernel route")
+            good = 0
+        # all ranks take the resident route or none does
+        flag = torch.tensor([good], dtype=torch.int32, device=self.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)  # also: every buffer is zeroed and mapped
+        self.ok = self.ok and bool(flag.item())
+
+    def status(self) -> int:
+        """0 = every launch so far saw all ranks; 1 = one timed out waiting (its results are NaN)."""
+        return int(_lib.load().plb_grid_exchange_status(self.buffer.data_ptr(), stream_ptr(self.device)))
+
+
 _peer_exchanges: dict = {}
 _peer_exchange_failed = False
 

@@ -18,11 +18,13 @@ Pass ``[FusedBatchTransforms(batch_transforms)]`` to the sampler instead of ``ba
 from __future__ import annotations
 
 import ctypes
+import os
 
 import torch
 
 from .. import _lib
 from .._leaves import Staging, previous_row, rows_2d, stream_ptr
+from ..arrays import DeviceArray
 from .advantage import EstimateAdvantage
 from .clip_rewards import ClipRewards
 from .norm_advantage import EPSILON as ADV_EPSILON
@@ -62,7 +64,10 @@ class FusedBatchTransforms(Transform):
         self._moments = None
         self._graphs: dict = {}
         self._seen: set = set()
-        self._bound: dict = {}  # (id(tree), phases) -> (probe leaves, their addresses, graph): replay fast path
+        # replay fast path: (signature of the leaves the tree holds NOW, phases) -> captured graph
+        self._bound: dict = {}
+        self._gx = None          # grid-exchange buffers of the resident advantage kernel
+        self._plans: dict = {}   # descriptor bytes -> plan bits agreed across the ranks
 
     # ------------------------------------------------------------------------------------
     def _distributed(self) -> bool:
@@ -73,21 +78,77 @@ class FusedBatchTransforms(Transform):
         from ..distributed import exchange_moments
         exchange_moments(moments, 1, 0, self.group)
 
+    _LEAF_NAMES = ("reward", "done", "advantage", "return_", "past_return", "valid", "bootstrap_value")
+
     @staticmethod
-    def _address(leaf) -> int:
-        """Cheap identity of the memory a device leaf currently exposes (window rotation included)."""
+    def _leaf_signature(leaf):
+        """What a captured graph depends on for one device leaf: the memory it exposes right now
+        (window rotation included) and its geometry.  None for host leaves."""
         if isinstance(leaf, torch.Tensor):
-            return leaf.data_ptr()
-        return leaf.base.data_ptr() + leaf._start  # DeviceArray: base buffer + window position
+            return (leaf.data_ptr(), leaf.shape, leaf.stride()) if leaf.is_cuda else None
+        if isinstance(leaf, DeviceArray):
+            base = leaf.base
+            return (base.data_ptr(), leaf._start, leaf._T, base.shape, leaf.padding)
+        return None
+
+    def _signature(self, sample_tree):
+        """Signature of the leaves `sample_tree` holds at this call, or None if any is not on the device.
+        Looked up afresh every call: a leaf replaced inside the same dict, or a new dict that happens to
+        reuse a dead one's id, must never replay a graph bound to other tensors."""
+        sig = []
+        for name in self._LEAF_NAMES:
+            if name in sample_tree:
+                one = self._leaf_signature(sample_tree[name])
+                if one is None:
+                    return None
+                sig.append(one)
+            else:
+                sig.append(None)
+        if "agent_info" in sample_tree and "value" in sample_tree["agent_info"]:
+            one = self._leaf_signature(sample_tree["agent_info"]["value"])
+            if one is None:
+                return None
+            sig.append(one)
+        return tuple(sig)
+
+    def _grid_exchange(self, dev):
+        """Buffers through which every CTA of every rank trades its partial advantage moments inside the
+        resident kernel; on one GPU a plain zeroed device buffer, on several a symmetric (peer-mapped) one."""
+        if self._gx is None or self._gx.device != dev:
+            from ..distributed import GridExchange
+            self._gx = GridExchange(self.group if self._distributed() else None, dev)
+        return self._gx
+
+    def _agree_plan(self, lib, d, key: bytes) -> int:
+        """Fused routes every rank can take: AND of the per-rank plans (uneven shards may differ in
+        alignment), computed once per descriptor -- a collective, so all ranks must bind the same trees
+        in the same order."""
+        plan = self._plans.get(key)
+        if plan is None:
+            plan = lib.plb_batch_pipeline_plan(ctypes.byref(d))
+            if plan < 0:
+                _lib.check(plan, "plb_batch_pipeline_plan")
+            if self._distributed():
+                import torch.distributed as dist
+                # bitwise AND as a MIN over one flag per route (NCCL has no BAND)
+                bits = (_lib.PLAN_CHUNKED, _lib.PLAN_RESIDENT)
+                t = torch.tensor([1 if plan & b else 0 for b in bits], dtype=torch.int32, device=self._ws.device)
+                dist.all_reduce(t, op=dist.ReduceOp.MIN, group=self.group)
+                plan = sum(b for b, on in zip(bits, t.tolist()) if on)
+            if len(self._plans) > 256:
+                self._plans.clear()
+            self._plans[key] = plan
+        return plan
 
     def __call__(self, sample_tree, phases: int = _lib.PHASE_ALL):
-        # fast path: this tree was captured before and none of its leaves moved -> replay the graph
+        # fast path: a graph was captured for exactly these leaves (same memory, same geometry) -> replay it;
         # inside somebody else's stream capture the launches are enqueued as they are (no nested graphs)
         capturing = torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()
-        bound = None if capturing else self._bound.get((id(sample_tree), phases))
-        if bound is not None:
-            leaves, addresses, graph = bound
-            if [self._address(leaf) for leaf in leaves] == addresses:
+        sig = None
+        if self.use_cuda_graph and not capturing and self._bound:
+            sig = self._signature(sample_tree)
+            graph = self._bound.get((sig, phases)) if sig is not None else None
+            if graph is not None:
                 graph.replay()
                 return sample_tree
         nr, est, na = self.norm_rewards, self.estimate, self.norm_adv
@@ -177,18 +238,37 @@ class FusedBatchTransforms(Transform):
         d.advantage_moments = self._moments.data_ptr() + 24
         d.workspace, d.workspace_bytes = self._ws.data_ptr(), self._ws.numel()
 
+        # routes: on one GPU the library picks (PLAN_AUTO); on several, what ALL ranks can do
+        distributed = self._distributed()
         in_kernel_exchange = False
-        if self._distributed() and phases == _lib.PHASE_ALL and not st.staged:
-            from ..distributed import get_peer_exchange
-            ex = get_peer_exchange(3, self.group, dev)
-            if ex is not None and ex.world <= 32:
-                d.xch_peers, d.xch_rank, d.xch_world = ex.peer_table.data_ptr(), ex.rank, ex.world
-                keep.append(ex)
-                in_kernel_exchange = True
+        d.plan = _lib.PLAN_AUTO
+        if distributed:
+            d.plan = 0
+            d.plan = self._agree_plan(lib, d, bytes(d) + bytes([phases]))
+        resident_ready = False
+        if phases == _lib.PHASE_ALL and (not st.staged or not distributed) and est is not None and na is not None \
+                and (d.plan & _lib.PLAN_RESIDENT) and os.environ.get("PLB_EXCHANGE", "p2p") == "p2p":
+            gx = self._grid_exchange(dev)
+            if gx.ok:
+                d.gx_peers, d.gx_rank, d.gx_world, d.gx_slots = gx.peer_table.data_ptr(), gx.rank, gx.world, gx.slots
+                keep.append(gx)
+                resident_ready = True
+        if distributed and not resident_ready:
+            d.plan &= ~_lib.PLAN_RESIDENT
+        if distributed and phases == _lib.PHASE_ALL and not st.staged:
+            if nr is None and resident_ready:
+                in_kernel_exchange = True  # the only statistic of this chain travels inside the resident kernel
+            elif d.plan & _lib.PLAN_CHUNKED:
+                from ..distributed import get_peer_exchange
+                ex = get_peer_exchange(3, self.group, dev)
+                if ex is not None and ex.world <= 32:
+                    d.xch_peers, d.xch_rank, d.xch_world = ex.peer_table.data_ptr(), ex.rank, ex.world
+                    keep.append(ex)
+                    in_kernel_exchange = True
 
         def enqueue():
             s = stream_ptr(dev)
-            if self._distributed() and phases == _lib.PHASE_ALL and not in_kernel_exchange:
+            if distributed and phases == _lib.PHASE_ALL and not in_kernel_exchange:
                 _lib.check(lib.plb_batch_pipeline_f32(ctypes.byref(d), _lib.PHASE_A, s), "fused transforms (A)")
                 if nr is not None:
                     self._exchange(self._moments[0:3])
@@ -213,7 +293,7 @@ class FusedBatchTransforms(Transform):
             graph = self._graphs.get(key)
             if graph is not None:
                 graph[0].replay()
-                self._bind(sample_tree, phases, graph[0])
+                self._bind(sample_tree, phases, graph[0], sig)
             elif key not in self._seen:
                 self._seen.add(key)  # first sight: run eagerly (also configures the kernels)
                 enqueue()
@@ -228,15 +308,12 @@ class FusedBatchTransforms(Transform):
         st.finish()
         return sample_tree
 
-    def _bind(self, sample_tree, phases: int, graph) -> None:
-        """Remember which device leaves this tree's graph depends on, for the replay fast path."""
-        names = ["reward", "done", "advantage", "return_", "past_return", "valid", "bootstrap_value"]
-        leaves = [sample_tree[n] for n in names if n in sample_tree]
-        if "agent_info" in sample_tree and "value" in sample_tree["agent_info"]:
-            leaves.append(sample_tree["agent_info"]["value"])
-        from ..arrays import DeviceArray
-        if not all(isinstance(x, (torch.Tensor, DeviceArray)) for x in leaves):
+    def _bind(self, sample_tree, phases: int, graph, sig=None) -> None:
+        """Remember the graph under the signature of the device leaves it was captured for."""
+        if sig is None:
+            sig = self._signature(sample_tree)
+        if sig is None:
             return
         if len(self._bound) > 256:
             self._bound.clear()
-        self._bound[(id(sample_tree), phases)] = (leaves, [self._address(x) for x in leaves], graph)
+        self._bound[(sig, phases)] = graph

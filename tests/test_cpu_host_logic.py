@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     for name in names:
         assert hasattr(lib, name), f"{name} declared in include/parllel_b200.h but not exported"
     bound = _lib.load()
-    assert bound.plb_version() == 100
+    assert bound.plb_version() == 200
 
 
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):

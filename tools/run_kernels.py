@@ -59,19 +59,19 @@ def main():
     ap.add_argument("--n", type=int, default=16384)
     ap.add_argument("--inner", type=int, default=1, help="launches per event pair (rotating buffer sets)")
     ap.add_argument("--rows", type=int, default=0)
-    ap.add_argument("--f32", type=int, default=0)
+    ap.add_argument("--resident", type=int, default=1, help="0: never take the resident (tensor-memory) advantage kernel")
+    ap.add_argument("--stages", type=int, default=0, help="cap on the input ring depth (0 = as many as fit)")
     ap.add_argument("--obs-variant", type=int, default=0)
     ap.add_argument("--debug", type=int, default=0)
     ap.add_argument("--obs-cols", type=int, default=16)
     ap.add_argument("--partials", type=int, default=1, help="gae_stats: publish per-CTA partials (as inside the fused step)")
-    ap.add_argument("--pipe", type=int, default=1, help="1: software-pipelined chunked scan, 0: two-phase")
     args = ap.parse_args()
     from parllel_b200 import _lib
     if args.rows:
         _lib.load().plb_set_tuning(0, args.rows)
-    _lib.load().plb_set_tuning(1, args.f32)
+    _lib.load().plb_set_tuning(12, args.resident)
+    _lib.load().plb_set_tuning(9, args.stages)
     _lib.load().plb_set_tuning(3, args.obs_variant)
-    _lib.load().plb_set_tuning(4, args.pipe)
     _lib.load().plb_set_tuning(5, args.debug)
     _lib.load().plb_set_tuning(7, args.obs_cols)
     dev = torch.device("cuda:0")
@@ -135,7 +135,7 @@ def main():
         raise SystemExit(f"unknown kernel {args.what}")
     us = sorted(us)
     med = us[len(us) // 2]
-    print(f"{args.what} T={T} B={B} algo={args.algo} rows={args.rows} f32={args.f32}: median {med:.2f} us  min {us[0]:.2f} us  "
+    print(f"{args.what} T={T} B={B} algo={args.algo} rows={args.rows} resident={args.resident} debug={args.debug} stages={args.stages}: median {med:.2f} us  min {us[0]:.2f} us  "
           f"-> {nbytes / med / 1e3:.1f} GB/s (median), {nbytes / us[0] / 1e3:.1f} GB/s (best)  [{nbytes} algorithmic bytes]")
 
 
