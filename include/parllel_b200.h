@@ -80,6 +80,7 @@ PLB_API int plb_sm_count(void);
  *   key 9: cap on the input ring depth of the chunked scan (0 = as many stages as fit)
  *   key 11: grid cap of the streaming normalise kernels, CTAs of 256 threads per SM (default 4)
  *   key 12: 0 = never take the resident (tensor-memory) advantage kernel (default 1)
+ *   key 13: 0 = index generation always by the single-CTA kernel (default 1: 8-CTA cluster kernel)
  * The environment variable PLB_TUNING="key=value,..." applies them when the Python package loads
  * the library. */
 #define PLB_TUNE_CHUNK_GEOMETRY 0
@@ -89,6 +90,7 @@ PLB_API int plb_sm_count(void);
 #define PLB_TUNE_SCAN_MAX_STAGES 9
 #define PLB_TUNE_NORMADV_CTAS_PER_SM 11
 #define PLB_TUNE_RESIDENT 12
+#define PLB_TUNE_RNG_CLUSTER 13
 PLB_API int plb_set_tuning(int key, int value);
 
 /* ------------------------------------------------------------------------------------

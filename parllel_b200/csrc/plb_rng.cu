@@ -12,12 +12,53 @@
 // Whether a raw 32-bit word is rejected depends only on the word itself, so the draw parallelises
 // exactly: every thread jumps the LCG ahead to its own word (O(log) 128-bit multiplies, then a fixed
 // stride), the accept flags are prefix-summed, and the first `n` accepted words are the result.
-// One CTA; the generator state lives in device memory and is advanced in place.
+// The generator state lives in device memory and is advanced in place.
+//
+// Two kernels: the usual ranges reject a word with probability < 2^-14, and there the whole draw is
+// speculated as one stream by a CLUSTER of eight 1024-thread CTAs (32768 words per round; the first
+// rejected word of a round is agreed through distributed shared memory, everything before it is final).
+// Every LCG jump comes from compile-time tables (plb_rng_tables.inc: M^d and the geometric sums G(d) do
+// not depend on the generator), so a launch costs a handful of 128-bit multiplies per thread instead of
+// O(log d) of them on a serial critical path.  Ranges just above a power of two (up to half of all words
+// rejected) take the single-CTA compaction kernel.
+#include <cooperative_groups.h>
+
 #include "plb_common.cuh"
 
 namespace plb {
 
+namespace cg = cooperative_groups;
+
 typedef unsigned __int128 u128;
+
+#include "plb_rng_tables.inc"
+
+struct Jump {
+    u128 m, g;  // s_d = m * s + inc * g
+};
+__device__ __forceinline__ Jump table_jump(const uint64_t (&e)[4])
+{
+    Jump j;
+    j.m = ((u128)e[0] << 64) | (u128)e[1];
+    j.g = ((u128)e[2] << 64) | (u128)e[3];
+    return j;
+}
+// `a` steps, then `b` steps
+__device__ __forceinline__ Jump compose(const Jump &a, const Jump &b)
+{
+    Jump r;
+    r.m = a.m * b.m;
+    r.g = b.m * a.g + b.g;
+    return r;
+}
+__device__ __forceinline__ u128 apply_jump(const Jump &j, u128 s, u128 inc) { return j.m * s + inc * j.g; }
+// arbitrary distance by binary decomposition (rare path: after a rejected word)
+__device__ __forceinline__ u128 jump_from(u128 s, u128 inc, uint64_t delta)
+{
+    for (int i = 0; delta != 0; ++i, delta >>= 1)
+        if (delta & 1) s = apply_jump(table_jump(RNG_POW2[i]), s, inc);
+    return s;
+}
 
 constexpr int RNG_THREADS = 1024;
 
@@ -373,6 +414,200 @@ __device__ void draw_stream(RngShared &sh, const RngParams &p, const StreamSpec 
     __syncthreads();
 }
 
+// ---------------------------------------------------------------------------------------------
+// Cluster version of draw_stream: eight CTAs speculate 32768 consecutive words per round.
+// ---------------------------------------------------------------------------------------------
+constexpr int CL_CTAS = 8;
+constexpr int CL_WORDS_PER_ROUND = CL_CTAS * RNG_THREADS * WORDS_PER_THREAD;  // 32768
+constexpr long long NO_REJECT = 1LL << 62;
+
+__global__ void __cluster_dims__(CL_CTAS, 1, 1) __launch_bounds__(RNG_THREADS)
+replay_indices_cluster_kernel(const RngParams p, const StreamSpec sp)
+{
+    __shared__ unsigned long long s_reject[2];  // first rejected word of the round, this CTA (by round parity)
+    __shared__ long long s_first;               // ... of the whole cluster
+    __shared__ u128 s_base;                     // generator state at output index pos >> 1 (after a restart)
+    cg::cluster_group cluster = cg::this_cluster();
+    const int cta = (int)cluster.block_rank();
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long gtid = (long long)cta * RNG_THREADS + tid;
+    const long long nthreads = (long long)CL_CTAS * RNG_THREADS;
+
+    const u128 s0 = ((u128)p.state[0] << 64) | (u128)p.state[1];
+    const u128 inc = ((u128)p.state[2] << 64) | (u128)p.state[3];
+    const int has = (int)(p.state[4] & 1ull);
+    const uint32_t buffered = (uint32_t)(p.state[4] >> 32);
+    if (tid == 0) { s_reject[0] = (unsigned long long)NO_REJECT; s_reject[1] = (unsigned long long)NO_REJECT; }
+
+    const long long n = p.n;
+    const int n_drawing = sp.draws[0] + sp.draws[1];
+    const long long total_out = (long long)n_drawing * n * p.k;
+    for (int which = 0; which < 2; ++which) {  // segments that consume no words (range 1)
+        if (!sp.draws[which]) {
+            int64_t *dst = which == 0 ? p.t_idx : p.b_idx;
+            const int64_t v = (which == 0 && sp.mod) ? (sp.add % sp.mod) : (which == 0 ? sp.add : 0);
+            for (long long i = gtid; i < n * p.k; i += nthreads) dst[i] = v;
+        }
+    }
+    struct Cursor {
+        long long mb, idx;
+        int which;
+    };
+    auto locate = [&](long long g) -> Cursor {
+        Cursor c;
+        const long long seg = g / n;
+        c.idx = g - seg * n;
+        c.mb = seg / n_drawing;
+        c.which = (n_drawing == 2) ? (int)(seg & 1) : (sp.draws[0] ? 0 : 1);
+        return c;
+    };
+    auto step = [&](Cursor &c) {
+        if (++c.idx == n) {
+            c.idx = 0;
+            if (n_drawing == 2) {
+                if (c.which == 1) ++c.mb;
+                c.which ^= 1;
+            } else {
+                ++c.mb;
+            }
+        }
+    };
+    auto rejected = [&](const Cursor &c, uint32_t w) -> bool {
+        if (sp.full_range[c.which]) return false;
+        return (uint32_t)((uint64_t)w * (uint64_t)sp.excl[c.which]) < sp.thr[c.which];
+    };
+    auto emit = [&](const Cursor &c, uint32_t w) {
+        int64_t v = sp.full_range[c.which] ? (int64_t)w : (int64_t)(((uint64_t)w * (uint64_t)sp.excl[c.which]) >> 32);
+        if (c.which == 0) {
+            if (sp.mod) {  // (v + add) % size_T with v < size_T and add < 2 * size_T
+                v += sp.add;
+                if (v >= sp.mod) v -= sp.mod;
+                if (v >= sp.mod) v -= sp.mod;
+            }
+            p.t_idx[c.mb * n + c.idx] = v;
+        } else {
+            p.b_idx[c.mb * n + c.idx] = v;
+        }
+    };
+    auto finish = [&](u128 ns, long long words) {  // exactly one thread of the cluster calls this
+        p.state[0] = (uint64_t)(ns >> 64);
+        p.state[1] = (uint64_t)ns;
+        const int h = (int)(words & 1);  // the high half of the last output stays buffered
+        p.state[4] = (uint64_t)h | ((uint64_t)(h ? (uint32_t)(xsl_rr(ns) >> 32) : 0u) << 32);
+    };
+
+    long long g0 = 0;  // outputs produced so far
+    bool done = total_out == 0;
+    if (!done && has) {  // the buffered half-word is the first word of the stream (every thread evaluates it alike)
+        const Cursor c0 = locate(0);
+        const bool ok = !rejected(c0, buffered);
+        if (ok && gtid == 0) emit(c0, buffered);
+        g0 = ok ? 1 : 0;
+        if (g0 >= total_out) {
+            if (gtid == 0) finish(s0, 0);
+            done = true;
+        }
+    }
+    if (done) {  // nothing (more) to draw: uniform over the cluster, so leaving before any barrier is safe
+        return;
+    }
+    // this thread's offset inside a round: outputs 2 * gtid and the two after it
+    const Jump mine = compose(table_jump(RNG_WARP[cta * 32 + warp]), table_jump(RNG_LANE[lane]));
+    const Jump stride = table_jump(RNG_POW2[14]);  // CL_WORDS_PER_ROUND / 2 = 16384 outputs per round
+    static_assert(CL_WORDS_PER_ROUND / 2 == (1 << 14), "round stride must match RNG_POW2[14]");
+    u128 st = apply_jump(mine, s0, inc);
+    long long pos = 0;  // fresh words consumed so far (word f = half f&1 of output f>>1)
+    int par = 0;
+    __syncthreads();
+    while (true) {
+        const long long f0 = pos + 4LL * gtid;  // this thread's first word of the round
+        const u128 st2 = st * pcg_mult() + inc;
+        const u128 st3 = st2 * pcg_mult() + inc;
+        const uint64_t o0 = xsl_rr(st), o1 = xsl_rr(st2), o2 = xsl_rr(st3);
+        uint32_t w[4];
+        if ((f0 & 1) == 0) {
+            w[0] = (uint32_t)o0; w[1] = (uint32_t)(o0 >> 32); w[2] = (uint32_t)o1; w[3] = (uint32_t)(o1 >> 32);
+        } else {
+            w[0] = (uint32_t)(o0 >> 32); w[1] = (uint32_t)o1; w[2] = (uint32_t)(o1 >> 32); w[3] = (uint32_t)o2;
+        }
+        // pass 1: the first word of the round that would be rejected at its speculative position
+        long long my_reject = NO_REJECT;
+        const long long gbase = g0 + (f0 - pos);
+        const Cursor cur0 = locate(gbase < total_out ? gbase : 0);
+        {
+            Cursor c = cur0;
+#pragma unroll
+            for (int kq = 0; kq < 4; ++kq) {
+                if (gbase + kq < total_out) {
+                    if (my_reject == NO_REJECT && rejected(c, w[kq])) my_reject = f0 + kq;
+                    step(c);
+                }
+            }
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            const long long o = __shfl_xor_sync(0xffffffffu, my_reject, d);
+            my_reject = o < my_reject ? o : my_reject;
+        }
+        if (lane == 0 && my_reject < NO_REJECT) atomicMin(&s_reject[par], (unsigned long long)my_reject);
+        cluster.sync();  // every CTA's minimum of this round is final
+        if (warp == 0) {
+            long long r = NO_REJECT;
+            if (lane < CL_CTAS) r = (long long)*cluster.map_shared_rank(&s_reject[par], lane);
+#pragma unroll
+            for (int d = 4; d > 0; d >>= 1) {
+                const long long o = __shfl_xor_sync(0xffffffffu, r, d);
+                r = o < r ? o : r;
+            }
+            if (lane == 0) {
+                s_first = r;
+                // last round's slot: every CTA passed this round's barrier, so nobody reads it any more
+                s_reject[par ^ 1] = (unsigned long long)NO_REJECT;
+            }
+        }
+        __syncthreads();
+        const long long first_reject = s_first;
+        // pass 2: everything before the first rejection (and inside the job) is final
+        {
+            Cursor c = cur0;
+#pragma unroll
+            for (int kq = 0; kq < 4; ++kq) {
+                const long long f = f0 + kq;
+                if (f < first_reject && gbase + kq < total_out) {
+                    emit(c, w[kq]);
+                    step(c);
+                }
+            }
+        }
+        const long long round_end = pos + CL_WORDS_PER_ROUND;
+        const long long stop = first_reject < round_end ? first_reject : round_end;  // words [pos, stop) accepted
+        const long long produced = stop - pos;
+        if (g0 + produced >= total_out) {  // the draw ends inside this round
+            const long long words = pos + (total_out - g0);  // fresh words consumed by the whole call
+            const long long last = words - 1;
+            if (last >= f0 && last < f0 + 4) {
+                // new state = the state that produced the last consumed output
+                const long long k_out = (last >> 1) - (f0 >> 1);
+                finish(k_out == 0 ? st : (k_out == 1 ? st2 : st3), words);
+            }
+            break;
+        }
+        g0 += produced;
+        par ^= 1;
+        if (first_reject < round_end) {
+            pos = first_reject + 1;  // the rejected word is consumed, nothing is produced for it
+            __syncthreads();         // s_base of an earlier restart has been read by everyone
+            if (tid == 0) s_base = jump_from(s0, inc, (uint64_t)(pos >> 1));
+            __syncthreads();
+            st = apply_jump(mine, s_base, inc);
+        } else {
+            pos = round_end;
+            st = apply_jump(stride, st, inc);
+        }
+    }
+    cluster.sync();  // no CTA may retire while a sibling can still read its shared memory
+}
+
 __global__ void __launch_bounds__(RNG_THREADS)
 replay_indices_kernel(const RngParams p)
 {
@@ -429,6 +664,9 @@ replay_indices_kernel(const RngParams p)
     }
 }
 
+static int g_rng_cluster = 1;  // 0: always the single-CTA kernel (plb_set_tuning key 13)
+void set_rng_cluster(int v) { g_rng_cluster = v; }
+
 }  // namespace plb
 
 extern "C" int plb_replay_sample_indices(uint64_t *pcg64_state, int64_t size_T, int64_t B, int64_t cursor, int full,
@@ -450,7 +688,25 @@ extern "C" int plb_replay_sample_indices(uint64_t *pcg64_state, int64_t size_T, 
     p.newest_invalid = newest_invalid; p.oldest_invalid = oldest_invalid;
     p.n = n; p.k = k;
     p.t_idx = t_idx; p.b_idx = b_idx;
-    replay_indices_kernel<<<1, RNG_THREADS, 0, (cudaStream_t)stream>>>(p);
+    // rejection rates of the two draws (same arithmetic as numpy's Lemire thresholds)
+    StreamSpec sp;
+    const uint64_t highs[2] = {(uint64_t)high_t, (uint64_t)B};
+    bool rare = true;
+    for (int i = 0; i < 2; ++i) {
+        const uint32_t rng = (uint32_t)(highs[i] - 1);
+        sp.draws[i] = rng != 0u;
+        sp.full_range[i] = rng == 0xFFFFFFFFu;
+        sp.excl[i] = rng + 1u;
+        sp.thr[i] = (sp.full_range[i] || rng == 0u) ? 0u : (uint32_t)((0xFFFFFFFFu - rng) % sp.excl[i]);
+        if (sp.thr[i] > (1u << 18)) rare = false;  // > 2^-14 per word
+    }
+    sp.add = full ? cursor + oldest_invalid : 0;
+    sp.mod = full ? size_T : 0;
+    if (rare && g_rng_cluster) {
+        replay_indices_cluster_kernel<<<CL_CTAS, RNG_THREADS, 0, (cudaStream_t)stream>>>(p, sp);
+    } else {
+        replay_indices_kernel<<<1, RNG_THREADS, 0, (cudaStream_t)stream>>>(p);
+    }
     PLB_LAUNCH_CHECK();
     return PLB_OK;
 }

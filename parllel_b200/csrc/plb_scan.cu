@@ -1148,6 +1148,7 @@ int plb_set_tuning(int key, int value)
     switch (key) {
         case 0: plb::g_chunked_geom = value; return PLB_OK;
         case 12: plb::g_resident = value; return PLB_OK;
+        case 13: plb::set_rng_cluster(value); return PLB_OK;
         case 5: plb::g_scan_debug = value; return PLB_OK;
         case 9: plb::g_scan_max_stages = value; return PLB_OK;
         case 11: plb::set_normadv_ctas_per_sm(value); return PLB_OK;

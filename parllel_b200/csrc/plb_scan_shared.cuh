@@ -118,6 +118,7 @@ int obs_variant();
 void set_obs_variant(int v);
 void set_normadv_ctas_per_sm(int v);
 void set_obs_lsu_cols(int v);
+void set_rng_cluster(int v);
 int obs_step_two_pass_l2(float *x, int64_t ld, int64_t rows, int64_t cols, const uint8_t *row_valid,
                          double *mean, double *var, const double *count, double *batch_count_out,
                          double eps, int flags, float clip_lo, float clip_hi, cudaStream_t stream);

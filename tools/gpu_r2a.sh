@@ -20,3 +20,5 @@ timeout 120 python tools/run_kernels.py gae --T 1024 --B 4096 --inner 24 --reps 
 timeout 120 python tools/run_kernels.py past --T 1024 --B 4096 --inner 24 --reps 15
 } > gpurun_out/r2a_timing.log 2>&1
 cat gpurun_out/r2a_timing.log
+timeout 300 python tools/time_replay.py default 13=0 > gpurun_out/r2a_replay.log 2>&1
+cat gpurun_out/r2a_replay.log
