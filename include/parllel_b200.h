@@ -80,6 +80,8 @@ PLB_API int plb_sm_count(void);
  *   key 9: cap on the input ring depth of the chunked scan (0 = as many stages as fit)
  *   key 11: grid cap of the streaming normalise kernels, CTAs of 256 threads per SM (default 4)
  *   key 12: 0 = never take the resident (tensor-memory) advantage kernel (default 1)
+ *   key 14 / 15: experiments on the resident kernel (1 = plain instead of cooperative launch / every thread polls)
+ *   key 16: 1 = replay gather through the load/store-unit path only (default 0: TMA-staged rows of >= 128 B)
  *   key 13: 0 = index generation always by the single-CTA kernel (default 1: 8-CTA cluster kernel)
  * The environment variable PLB_TUNING="key=value,..." applies them when the Python package loads
  * the library. */
@@ -92,6 +94,10 @@ PLB_API int plb_sm_count(void);
 #define PLB_TUNE_RESIDENT 12
 #define PLB_TUNE_RNG_CLUSTER 13
 PLB_API int plb_set_tuning(int key, int value);
+/* Diagnostics: with a DEVICE buffer of >= 8 * 8 * plb_sm_count() bytes set, every CTA of the resident
+ * advantage kernel leaves %globaltimer stamps there ([cta][8]: start, scan done, published, collected,
+ * stores issued, stores drained); NULL (default) switches it off. */
+PLB_API void plb_debug_set_buffer(void *device_buffer);
 
 /* ------------------------------------------------------------------------------------
  * EstimateAdvantage            parllel/transforms/advantage.py:36-57 (compute_gae_advantage)
@@ -224,6 +230,11 @@ PLB_API int plb_normalize_advantage_f32(
 PLB_API int plb_normalize_columns_f32(
     float *x, int64_t ld_x, int64_t rows, int64_t cols,
     const double *mean, const double *var, double eps, plb_stream_t stream);
+
+/* same pass with the clamp EXTENSION of plb_normalize_observations_step_f32 fused in (NaN = no bound) */
+PLB_API int plb_normalize_columns_clip_f32(
+    float *x, int64_t ld_x, int64_t rows, int64_t cols,
+    const double *mean, const double *var, double eps, double clip_lo, double clip_hi, plb_stream_t stream);
 
 /* NormalizeObservations.__call__ for one step   parllel/transforms/norm_obs.py:57-76
  * update running stats from obs[row_valid] FIRST, then normalise all rows with the

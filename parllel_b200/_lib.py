@@ -66,6 +66,7 @@ _SIGNATURES = {
     "plb_sm_count": ([], c_int),
     "plb_launch_counters": ([ctypes.POINTER(c_int64)], None),
     "plb_set_tuning": ([c_int, c_int], c_int),
+    "plb_debug_set_buffer": ([c_void_p], None),
     "plb_compute_gae_advantage_f32": (
         [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64,
          c_int64, c_int64, c_int64, c_double, c_double, c_int, c_void_p], c_int),
@@ -97,6 +98,8 @@ _SIGNATURES = {
         [c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_double, c_void_p], c_int),
     "plb_normalize_columns_f32": (
         [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_double, c_void_p], c_int),
+    "plb_normalize_columns_clip_f32": (
+        [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_double, c_double, c_double, c_void_p], c_int),
     "plb_normalize_observations_workspace_bytes": ([c_int64, c_int64], c_size_t),
     "plb_normalize_observations_step_f32": (
         [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_int,

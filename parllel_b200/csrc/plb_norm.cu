@@ -109,15 +109,16 @@ struct NormAdvOp {
     const double *moments;  // [inner][3]
     int64_t inner;
     float eps;
-    float mean0, denom0;    // single-agent case, hoisted
+    float mean0, denom0, rdenom0;    // single-agent case, hoisted
     __device__ __forceinline__ void prepare()
     {
         mean0 = __double2float_rn(moments[1]);
         denom0 = __fadd_rn(__double2float_rn(sqrt(moments[2] / moments[0])), eps);
+        rdenom0 = __frcp_rn(denom0);
     }
     __device__ __forceinline__ float operator()(float x, int64_t col) const
     {
-        if (inner == 1) return __fdiv_rn(__fsub_rn(x, mean0), denom0);
+        if (inner == 1) return div_by(__fsub_rn(x, mean0), denom0, rdenom0);
         const double *m = moments + 3 * (col % inner);
         const float mean = __double2float_rn(m[1]);
         const float stdv = __double2float_rn(sqrt(m[2] / m[0]));
@@ -177,7 +178,7 @@ normalize_advantage_partials_kernel(float *__restrict__ x, int64_t ld_x, int64_t
         }
     }
     __syncthreads();
-    const float mean = s_mean, denom = s_denom;
+    const float mean = s_mean, denom = s_denom, rdenom = __frcp_rn(s_denom);
     for (int64_t base = tid; base < total; base += nthreads * U) {
         if (base != tid) {
 #pragma unroll
@@ -195,10 +196,10 @@ normalize_advantage_partials_kernel(float *__restrict__ x, int64_t ld_x, int64_t
             const int64_t i = base + (int64_t)u * nthreads;
             if (i < total) {
                 float4 o;
-                o.x = __fdiv_rn(__fsub_rn(v[u].x, mean), denom);
-                o.y = __fdiv_rn(__fsub_rn(v[u].y, mean), denom);
-                o.z = __fdiv_rn(__fsub_rn(v[u].z, mean), denom);
-                o.w = __fdiv_rn(__fsub_rn(v[u].w, mean), denom);
+                o.x = div_by(__fsub_rn(v[u].x, mean), denom, rdenom);
+                o.y = div_by(__fsub_rn(v[u].y, mean), denom, rdenom);
+                o.z = div_by(__fsub_rn(v[u].z, mean), denom, rdenom);
+                o.w = div_by(__fsub_rn(v[u].w, mean), denom, rdenom);
                 *reinterpret_cast<float4 *>(x + off[u]) = o;
             }
         }
@@ -239,7 +240,7 @@ normalize_advantage_xch_kernel(float *__restrict__ x, int64_t ld_x, int64_t rows
         }
     }
     __syncthreads();
-    const float mean = s_mean, denom = s_denom;
+    const float mean = s_mean, denom = s_denom, rdenom = __frcp_rn(s_denom);
     for (int64_t base = tid; base < total; base += nthreads * U) {
         if (base != tid) {
 #pragma unroll
@@ -257,10 +258,10 @@ normalize_advantage_xch_kernel(float *__restrict__ x, int64_t ld_x, int64_t rows
             const int64_t i = base + (int64_t)u * nthreads;
             if (i < total) {
                 float4 o;
-                o.x = __fdiv_rn(__fsub_rn(v[u].x, mean), denom);
-                o.y = __fdiv_rn(__fsub_rn(v[u].y, mean), denom);
-                o.z = __fdiv_rn(__fsub_rn(v[u].z, mean), denom);
-                o.w = __fdiv_rn(__fsub_rn(v[u].w, mean), denom);
+                o.x = div_by(__fsub_rn(v[u].x, mean), denom, rdenom);
+                o.y = div_by(__fsub_rn(v[u].y, mean), denom, rdenom);
+                o.z = div_by(__fsub_rn(v[u].z, mean), denom, rdenom);
+                o.w = div_by(__fsub_rn(v[u].w, mean), denom, rdenom);
                 *reinterpret_cast<float4 *>(x + off[u]) = o;
             }
         }
@@ -452,6 +453,14 @@ int plb_normalize_columns_f32(float *x, int64_t ld_x, int64_t rows, int64_t cols
                               const double *var, double eps, plb_stream_t stream)
 {
     return plb::normalize_columns(x, ld_x, rows, cols, mean, var, eps, -INFINITY, INFINITY, (cudaStream_t)stream);
+}
+
+int plb_normalize_columns_clip_f32(float *x, int64_t ld_x, int64_t rows, int64_t cols, const double *mean,
+                                   const double *var, double eps, double clip_lo, double clip_hi, plb_stream_t stream)
+{
+    const float lo = (clip_lo != clip_lo) ? -INFINITY : (float)clip_lo;
+    const float hi = (clip_hi != clip_hi) ? INFINITY : (float)clip_hi;
+    return plb::normalize_columns(x, ld_x, rows, cols, mean, var, eps, lo, hi, (cudaStream_t)stream);
 }
 
 size_t plb_normalize_observations_workspace_bytes(int64_t rows, int64_t cols)

@@ -223,7 +223,9 @@ struct Params {
     double *adv_moments_out;
     float *out0_raw; int64_t ld_out0_raw;   // out0 as a plain pointer (ragged rows of the final store phase)
     int tmem_cols;                // TMEM columns to allocate: power of two >= tiles per CTA x 2 x R
-    int n_out_bufs;               // staging buffers of the final store phase carved from the input ring (2 or 4)
+    unsigned long long *dbg;      // experiments: per-CTA phase timestamps [grid][8] (plb_debug_set_buffer), or NULL
+    int poll_mode;                // 0: arrival hint, then one batched read of the records (default); 1: no hint, poll the records
+    int n_out_bufs;               // whole-tile staging buffers of the final store phase carved from the input ring
 };
 
 struct TensorMaps {
@@ -233,8 +235,6 @@ struct TensorMaps {
     // negative row.  TMA loads zero-fill there, but a TMA STORE may not start out of bounds:
     // that ragged tile is stored through maps whose box is only T % TC rows tall, from row 0.
     CUtensorMap o0_rag, o1_rag, o2_rag;
-    // resident variant: out0 with a box of one warp's R rows (every warp stores its own slab)
-    CUtensorMap o0_warp;
 };
 
 __device__ __forceinline__ float to_f32(double x) { return __double2float_rn(x); }
@@ -288,6 +288,7 @@ scan_pipelined_kernel(const __grid_constant__ TensorMaps tm, const Params p)
     const int64_t T = p.T;
 
     __shared__ uint32_t s_tmem_base, s_epoch;
+    if (RESIDENT && p.dbg != nullptr && threadIdx.x == 0) p.dbg[blockIdx.x * 8 + 0] = global_timer_ns();
     if (threadIdx.x == 0) {
         for (int s = 0; s < n_stages; ++s) mbar_init(&sh->full[s], 1);
         fence_proxy_async_smem();
@@ -596,22 +597,24 @@ scan_pipelined_kernel(const __grid_constant__ TensorMaps tm, const Params p)
     // after the last body: the final tile sits in outs[par ^ 1]
     if (threadIdx.x == 0 && st_pending) store_tile(par ^ 1);
     if constexpr (RESIDENT) {
-        // ---- statistics of the whole batch: publish this CTA's moments, collect everybody's -------
-        __shared__ double s_pub[3];
+        // ---- statistics of the whole batch: publish this CTA's sums, collect everybody's -------------
+        __shared__ double s_pub[GX_RECORD_VALS];
         __shared__ float s_mean, s_denom;
         const uint32_t epoch = s_epoch;
+        if (p.dbg != nullptr && threadIdx.x == 0) p.dbg[blockIdx.x * 8 + 1] = global_timer_ns();
         Sums acc;
         acc.n = (double)st_n; acc.s1 = st_s1; acc.s2 = st_s2; acc.piv = (double)st_piv;
         const Sums blk = block_reduce_sums_warp_pivot(acc, red_scratch);
-        if (threadIdx.x == 0) {
-            const Moments m = to_moments(blk);
-            s_pub[0] = m.n; s_pub[1] = m.mean; s_pub[2] = m.m2;
-        }
+        if (threadIdx.x == 0) { s_pub[0] = blk.n; s_pub[1] = blk.s1; s_pub[2] = blk.s2; s_pub[3] = blk.piv; }
         __syncthreads();
         gx_publish(p.gx, epoch, s_pub);
-        static_assert(sizeof(Moments) <= sizeof(Sums), "warp scratch is reused for Moments");
-        const Moments all = gx_collect(p.gx, epoch, reinterpret_cast<Moments *>(red_scratch));
+        if (p.dbg != nullptr && threadIdx.x == 0) p.dbg[blockIdx.x * 8 + 2] = global_timer_ns();
+        // one thread waits for the arrival hint (cheap to poll), then everybody reads its records in one batch
+        if (p.poll_mode == 0 && threadIdx.x == 0) gx_wait_arrivals(p.gx, epoch);
+        __syncthreads();
+        const Moments all = gx_collect(p.gx, epoch, red_scratch);
         if (threadIdx.x == 0) {
+            if (p.dbg != nullptr) p.dbg[blockIdx.x * 8 + 3] = global_timer_ns();
             s_mean = __double2float_rn(all.mean);
             s_denom = __fadd_rn(__double2float_rn(sqrt(all.m2 / all.n)), p.adv_eps);
             if (blockIdx.x == 0) {
@@ -620,51 +623,58 @@ scan_pipelined_kernel(const __grid_constant__ TensorMaps tm, const Params p)
             gx_retire(p.gx, epoch);
         }
         __syncthreads();
-        const float mean = s_mean, denom = s_denom;
+        const float mean = s_mean, denom = s_denom, rdenom = __frcp_rn(s_denom);
         // ---- advantage = (adv - mean) / (std + eps), float32 (norm_advantage.py:51-54), stored once --
         tmem_wait_st();
-        // the input ring is idle now (every requested tile has been consumed): its first bytes become
-        // per-warp staging slabs for the TMA stores, `n_out_bufs` tiles deep
-        float *slabs = reinterpret_cast<float *>(smem_raw);
+        // The input ring is idle now (every requested tile has been consumed): it becomes `n_out_bufs` whole-tile
+        // staging buffers.  Rounds of up to n_out_bufs tiles: all warps fill their slabs of every tile of the round
+        // from tensor memory, one barrier, then one tile-sized TMA store per tile (the TMA clips the columns beyond
+        // B; the tile that starts before t = 0 goes through the ragged map, as in the scan).
+        float *bufs = reinterpret_cast<float *>(smem_raw);
         const int n_bufs = p.n_out_bufs;
-        int n_tma = 0;  // slabs this warp has handed to the TMA so far
-        for (int j = 0; j < n_tiles; ++j) {
-            const int strip = (int)blockIdx.x + (j / n_chunks) * (int)gridDim.x;
-            const int k = j - (j / n_chunks) * n_chunks;
-            const int64_t row0 = T - (int64_t)(k + 1) * TC + i0;  // first row of this warp's slab
-            float x[R];
-            tmem_ld<R>(tmem_warp + (uint32_t)(j * 2 * R), x);
+        for (int j0 = 0; j0 < n_tiles; j0 += n_bufs) {
+            const int j1 = (j0 + n_bufs < n_tiles) ? j0 + n_bufs : n_tiles;
+            if (j0 > 0) {  // the previous round's stores must have read the buffers
+                if (threadIdx.x == 0) tma_store_wait_read<0>();
+                __syncthreads();
+            }
+            for (int j = j0; j < j1; ++j) {
+                float x[R];
+                tmem_ld<R>(tmem_warp + (uint32_t)(j * 2 * R), x);
+                float *slab = bufs + ((size_t)(j - j0) * TC + i0) * W;
+                if (!(p.debug & 4)) {
 #pragma unroll
-            for (int u = 0; u < R; ++u) x[u] = __fdiv_rn(__fsub_rn(x[u], mean), denom);
-            if (row0 >= 0 && !(p.debug & 4)) {
-                float *slab = slabs + ((size_t)(n_tma % n_bufs) * TC + i0) * W;
-                if (n_tma >= n_bufs) {  // the slab was handed to the TMA n_bufs stores ago: it must have been read
-                    if (lane == 0) {
-                        if (n_bufs == 4) tma_store_wait_read<3>();
-                        else tma_store_wait_read<1>();
+                    for (int u = 0; u < R; ++u) slab[u * W + lane] = div_by(__fsub_rn(x[u], mean), denom, rdenom);
+                } else {  // experiment switch: plain coalesced stores straight from registers
+                    const int strip = (int)blockIdx.x + (j / n_chunks) * (int)gridDim.x;
+                    const int k = j - (j / n_chunks) * n_chunks;
+                    const int64_t row0 = T - (int64_t)(k + 1) * TC + i0;
+                    const int64_t col = (int64_t)strip * W + lane;
+                    if (col < p.B) {
+#pragma unroll
+                        for (int u = 0; u < R; ++u)
+                            if (row0 + u >= 0)
+                                p.out0_raw[(row0 + u) * p.ld_out0_raw + col] = div_by(__fsub_rn(x[u], mean), denom, rdenom);
                     }
-                    __syncwarp();
-                }
-#pragma unroll
-                for (int u = 0; u < R; ++u) slab[u * W + lane] = x[u];
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) {
-                    tma_store_2d(&tm.o0_warp, slab, strip * W, (int)row0);
-                    tma_store_commit();
-                }
-                ++n_tma;
-            } else {
-                // ragged first rows of the batch (or the experiment switch): plain coalesced stores
-                const int64_t col = (int64_t)strip * W + lane;
-                if (col < p.B) {
-#pragma unroll
-                    for (int u = 0; u < R; ++u)
-                        if (row0 + u >= 0) p.out0_raw[(row0 + u) * p.ld_out0_raw + col] = x[u];
                 }
             }
+            fence_proxy_async_smem();
+            __syncthreads();
+            if (threadIdx.x == 0 && !(p.debug & 4)) {
+                for (int j = j0; j < j1; ++j) {
+                    const int strip = (int)blockIdx.x + (j / n_chunks) * (int)gridDim.x;
+                    const int k = j - (j / n_chunks) * n_chunks;
+                    const int t0 = (int)T - (k + 1) * TC;
+                    const float *tile = bufs + (size_t)(j - j0) * TC * W;
+                    if (t0 < 0) tma_store_2d(&tm.o0_rag, tile + (size_t)(-t0) * W, strip * W, 0);
+                    else tma_store_2d(&tm.o0, tile, strip * W, t0);
+                }
+                tma_store_commit();
+            }
         }
-        if (lane == 0) tma_store_wait<0>();  // shared memory must outlive the bulk reads
+        if (p.dbg != nullptr && threadIdx.x == 0) p.dbg[blockIdx.x * 8 + 4] = global_timer_ns();
+        if (threadIdx.x == 0) tma_store_wait<0>();  // shared memory must outlive the bulk reads
+        if (p.dbg != nullptr && threadIdx.x == 0) p.dbg[blockIdx.x * 8 + 5] = global_timer_ns();
         tmem_fence_before_sync();
         __syncthreads();
         if (warp == 0) {
@@ -758,6 +768,9 @@ static int g_chunked_geom = 0;
 static int g_scan_debug = 0;
 static int g_scan_max_stages = 0;     // experiments: cap on the input ring depth (plb_set_tuning key 9)
 static int g_resident = 1;            // 0: never take the resident (TMEM) variant (plb_set_tuning key 12)
+static int g_resident_plain_launch = 0;  // experiments: 1 = no cooperative-launch attribute (key 14)
+static int g_resident_poll = 0;          // experiments: 1 = every thread polls its own records (key 15)
+static unsigned long long *g_debug_buf = nullptr;  // plb_debug_set_buffer
 
 template <int MODE, typename ACC, int NW, int R, bool HAS_PRE, bool HAS_STATS>
 static int launch_chunked_inst(const chunked::TensorMaps &tm, chunked::Params p, int sms, cudaStream_t stream)
@@ -861,8 +874,8 @@ static int launch_resident_inst(const chunked::TensorMaps &tm, chunked::Params p
     p.debug = g_scan_debug;
     p.tmem_cols = geo.tmem_cols;
     const size_t tile_bytes = (size_t)TC * W * sizeof(float);
-    p.n_out_bufs = (stage_bytes * stages >= 4 * tile_bytes) ? 4 : 2;
-    PLB_REQUIRE(stage_bytes * stages >= 2 * tile_bytes, PLB_ERR_UNSUPPORTED, "resident scan: ring too small for the store phase");
+    p.n_out_bufs = (int)(stage_bytes * stages / tile_bytes);  // whole-tile staging buffers the idle ring holds
+    PLB_REQUIRE(p.n_out_bufs >= 1, PLB_ERR_UNSUPPORTED, "resident scan: ring too small for the store phase");
     const size_t smem = stage_bytes * stages + fixed_bytes;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)geo.grid);
@@ -873,7 +886,9 @@ static int launch_resident_inst(const chunked::TensorMaps &tm, chunked::Params p
     attr[0].id = cudaLaunchAttributeCooperative;  // every CTA waits for every other: the grid must be co-resident
     attr[0].val.cooperative = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = g_resident_plain_launch ? 0 : 1;
+    p.dbg = g_debug_buf;
+    p.poll_mode = g_resident_poll;
     PLB_CUDA(cudaLaunchKernelEx(&cfg, kern, tm, p));
     count_launch(1);
     return PLB_OK;
@@ -931,11 +946,7 @@ static int build_tensor_maps(const ChunkedIO &io, const chunked::Params &p, bool
             if (rc) return rc;
         }
     }
-    tm.o0_warp = tm.o0;
-    if (warp_rows > 0) {
-        rc = make_tensor_map_2d(&tm.o0_warp, io.out0, 4, p.T, p.B, io.ld0, warp_rows, W);
-        if (rc) return rc;
-    }
+    (void)warp_rows;
     return PLB_OK;
 }
 
@@ -1149,6 +1160,9 @@ int plb_set_tuning(int key, int value)
         case 0: plb::g_chunked_geom = value; return PLB_OK;
         case 12: plb::g_resident = value; return PLB_OK;
         case 13: plb::set_rng_cluster(value); return PLB_OK;
+        case 16: plb::set_gather_mode(value); return PLB_OK;
+        case 14: plb::g_resident_plain_launch = value; return PLB_OK;
+        case 15: plb::g_resident_poll = value; return PLB_OK;
         case 5: plb::g_scan_debug = value; return PLB_OK;
         case 9: plb::g_scan_max_stages = value; return PLB_OK;
         case 11: plb::set_normadv_ctas_per_sm(value); return PLB_OK;
@@ -1157,6 +1171,8 @@ int plb_set_tuning(int key, int value)
         default: plb::set_error("unknown tuning key %d", key); return PLB_ERR_INVALID_ARGUMENT;
     }
 }
+
+void plb_debug_set_buffer(void *device_buffer) { plb::g_debug_buf = reinterpret_cast<unsigned long long *>(device_buffer); }
 
 int plb_compute_gae_advantage_f32(const float *reward, int64_t ld_reward, const float *value, int64_t ld_value,
                                   const uint8_t *done, int64_t ld_done, const float *bootstrap_value,

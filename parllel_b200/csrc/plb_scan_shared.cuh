@@ -59,14 +59,18 @@ static inline MomentsTail make_tail(double *moments_out, void *workspace)
 // order -- so the grid barrier of one GPU and the all-gather across GPUs are the same step, with no
 // atomics, no last-CTA reduction and no second kernel.  Buffer layout (plb_grid_exchange_bytes):
 //     uint32 epoch @0 | uint32 exit_ticket @4 | uint32 status @8 (0 ok, 1 timed out)
-//     records @256: [2 (epoch parity)][world][slots] x 48 B = 3 x {lo, epoch, hi, epoch} 16-byte units
+//     uint32 arrived[2] @16 (by epoch parity): slots filled so far, a HINT for when to read -- the
+//            records validate themselves through their epoch tags, so no fence orders it after them
+//     records @256: [2 (epoch parity)][world][slots] x 64 B = 4 x {lo, epoch, hi, epoch} 16-byte units
+//            carrying the division-free Sums (n, s1, s2, pivot) of one CTA
 struct GridXch {
     unsigned char *const *peers;  // device array [world]: every rank's buffer (world == 1: just ours)
     int rank, world;
     int slots;                    // records per rank and epoch (>= the largest grid of any rank)
 };
 constexpr size_t GX_HEADER_BYTES = 256;
-constexpr size_t GX_RECORD_BYTES = 48;
+constexpr size_t GX_RECORD_BYTES = 64;
+constexpr int GX_RECORD_VALS = 4;
 constexpr int GX_MAX_WORLD = 32;
 constexpr int GX_MAX_SLOTS = 1024;
 __host__ __device__ __forceinline__ size_t gx_total_bytes(int world, int slots)
@@ -119,6 +123,7 @@ void set_obs_variant(int v);
 void set_normadv_ctas_per_sm(int v);
 void set_obs_lsu_cols(int v);
 void set_rng_cluster(int v);
+void set_gather_mode(int v);
 int obs_step_two_pass_l2(float *x, int64_t ld, int64_t rows, int64_t cols, const uint8_t *row_valid,
                          double *mean, double *var, const double *count, double *batch_count_out,
                          double eps, int flags, float clip_lo, float clip_hi, cudaStream_t stream);
@@ -393,6 +398,16 @@ __device__ __forceinline__ void tmem_ld(uint32_t taddr, float (&x)[N])
     tmem_wait_ld();
 }
 
+// x / d through the correctly rounded reciprocal r = 1/d and one FMA residual step (Markstein): the IEEE
+// quotient except in rare double-rounding cases (1 ulp), at 3 instructions instead of the ~30 of the
+// division subroutine -- the normalise passes divide every element by the same denominator.
+__device__ __forceinline__ float div_by(float x, float d, float r)
+{
+    const float q = x * r;
+    const float e = fmaf(-q, d, x);
+    return (fabsf(q) < INFINITY) ? fmaf(e, r, q) : q;
+}
+
 // ---------------------------------------------------------------------------------
 // Grid exchange (see GridXch above).  gx_epoch / gx_publish / gx_collect / gx_retire are called by
 // every CTA of the launch, in that order; all ranks must issue the same sequence of launches on one
@@ -408,7 +423,7 @@ __device__ __forceinline__ unsigned char *gx_record(unsigned char *buf, const Gr
     return buf + GX_HEADER_BYTES + (((size_t)(epoch & 1u) * g.world + src_rank) * g.slots + slot) * GX_RECORD_BYTES;
 }
 
-// Publish this CTA's moments (read from `mine`, e.g. shared memory, by every participating thread) into
+// Publish this CTA's Sums (n, s1, s2, pivot -- read from `mine`, e.g. shared memory, by every participating thread) into
 // slot blockIdx.x of every rank, and empty records into the slots no CTA of this grid owns
 // (blockIdx.x + k * gridDim.x < slots).  Call with all threads of the CTA.
 __device__ __forceinline__ void gx_publish(const GridXch &g, uint32_t epoch, const double *mine)
@@ -419,46 +434,78 @@ __device__ __forceinline__ void gx_publish(const GridXch &g, uint32_t epoch, con
         const int slot = (int)blockIdx.x + k * (int)gridDim.x;
         unsigned char *dst = gx_record(g.peers[r], g, epoch, g.rank, slot);
 #pragma unroll
-        for (int v = 0; v < 3; ++v) {
+        for (int v = 0; v < GX_RECORD_VALS; ++v) {
             const unsigned long long bits = (k == 0) ? (unsigned long long)__double_as_longlong(mine[v]) : 0ull;
             asm volatile("st.relaxed.sys.global.v4.u32 [%0], {%1, %2, %3, %4};"
                          ::"l"(dst + 16 * v), "r"((uint32_t)bits), "r"(epoch), "r"((uint32_t)(bits >> 32)), "r"(epoch)
                          : "memory");
         }
     }
+    __syncthreads();  // the record stores of all threads are issued before the arrival hints
+    if ((int)threadIdx.x < g.world) {
+        uint32_t *cnt = reinterpret_cast<uint32_t *>(g.peers[threadIdx.x]) + 4 + (epoch & 1u);
+        asm volatile("red.relaxed.sys.global.add.u32 [%0], %1;" ::"l"(cnt), "r"((uint32_t)extra) : "memory");
+    }
 }
 
-// Wait for all world x slots records of `epoch` in this rank's buffer and merge them.  Records are
-// dealt to threads round-robin; each thread keeps up to four polls in flight (one L2 round trip per
-// batch), merges its records in index order, then lanes and warps merge in index order: the same
-// operations on the same data in every CTA of every rank, so all of them derive identical bits.
-// Returns the merged moments in thread 0 (other threads: partial).  `warp_scratch` >= 32 Moments.
-__device__ __forceinline__ Moments gx_collect(const GridXch &g, uint32_t epoch, Moments *warp_scratch)
+// Wait until the arrival hint says every slot of `epoch` has been filled (one thread per CTA spins on one
+// word with back-off: hundreds of CTAs polling whole record arrays would congest the very L2 lines the
+// late CTAs' records have to reach).  Returns false on timeout.
+__device__ __forceinline__ bool gx_wait_arrivals(const GridXch &g, uint32_t epoch)
+{
+    const uint32_t *cnt = reinterpret_cast<const uint32_t *>(g.peers[g.rank]) + 4 + (epoch & 1u);
+    const uint32_t want = (uint32_t)(g.world * g.slots);
+    const long long t_start = clock64();
+    unsigned ns = 20;
+    while (true) {
+        uint32_t v;
+        asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(cnt) : "memory");
+        if (v >= want) return true;
+        if (clock64() - t_start > 20000000000LL) return false;
+        __nanosleep(ns);
+        if (ns < 160) ns <<= 1;
+    }
+}
+
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Wait for all world x slots records of `epoch` in this rank's buffer and add them up.  Records are dealt
+// to threads round-robin; each thread keeps up to four polls in flight (one L2 round trip per batch) and
+// adds its records in index order around the first pivot it meets (rebase: no divisions anywhere), then
+// the block reduction agrees on one pivot and adds in a fixed order: the same operations on the same data
+// in every CTA of every rank, so all of them derive identical bits.  Result (as moments: the only
+// divisions of the whole exchange) in thread 0.  `scratch` >= 32 Sums.  All threads of the CTA must call.
+__device__ __forceinline__ Moments gx_collect(const GridXch &g, uint32_t epoch, Sums *scratch)
 {
     unsigned char *mine = g.peers[g.rank];
     const int n_rec = g.world * g.slots;
-    Moments acc;
-    acc.n = 0.0; acc.mean = 0.0; acc.m2 = 0.0;
+    Sums acc;
+    acc.n = 0.0; acc.s1 = 0.0; acc.s2 = 0.0; acc.piv = 0.0;
     const long long t_start = clock64();
     bool timed_out = false;
     for (int base = threadIdx.x; base < n_rec; base += 4 * blockDim.x) {
-        double v[4][3];
+        double v[4][GX_RECORD_VALS];
         unsigned pending = 0u;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             if (base + j * (int)blockDim.x < n_rec) pending |= 1u << j;
 #pragma unroll
-            for (int c = 0; c < 3; ++c) v[j][c] = 0.0;
+            for (int c = 0; c < GX_RECORD_VALS; ++c) v[j][c] = 0.0;
         }
         while (pending != 0u) {
-            uint4 q[4][3];
+            uint4 q[4][GX_RECORD_VALS];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 if (pending & (1u << j)) {
                     const int idx = base + j * (int)blockDim.x;  // = src_rank * slots + slot
                     const unsigned char *src = mine + GX_HEADER_BYTES + ((size_t)(epoch & 1u) * n_rec + idx) * GX_RECORD_BYTES;
 #pragma unroll
-                    for (int c = 0; c < 3; ++c)
+                    for (int c = 0; c < GX_RECORD_VALS; ++c)
                         asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];"
                                      : "=r"(q[j][c].x), "=r"(q[j][c].y), "=r"(q[j][c].z), "=r"(q[j][c].w)
                                      : "l"(src + 16 * c)
@@ -470,10 +517,10 @@ __device__ __forceinline__ Moments gx_collect(const GridXch &g, uint32_t epoch, 
                 if (pending & (1u << j)) {
                     bool ok = true;
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) ok = ok && q[j][c].y == epoch && q[j][c].w == epoch;
+                    for (int c = 0; c < GX_RECORD_VALS; ++c) ok = ok && q[j][c].y == epoch && q[j][c].w == epoch;
                     if (ok) {
 #pragma unroll
-                        for (int c = 0; c < 3; ++c)
+                        for (int c = 0; c < GX_RECORD_VALS; ++c)
                             v[j][c] = __longlong_as_double((long long)(((unsigned long long)q[j][c].z << 32) | (unsigned long long)q[j][c].x));
                         pending &= ~(1u << j);
                     }
@@ -486,32 +533,24 @@ __device__ __forceinline__ Moments gx_collect(const GridXch &g, uint32_t epoch, 
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            Moments m;
-            m.n = v[j][0]; m.mean = v[j][1]; m.m2 = v[j][2];
-            acc = merge(acc, m);
+            Sums q;
+            q.n = v[j][0]; q.s1 = v[j][1]; q.s2 = v[j][2]; q.piv = v[j][3];
+            if (q.n > 0.0) {
+                if (acc.n == 0.0) acc = q;
+                else {
+                    q = rebase(q, acc.piv);
+                    acc.n += q.n; acc.s1 += q.s1; acc.s2 += q.s2;
+                }
+            }
         }
         if (timed_out) break;
     }
-    if (timed_out) {  // no trap: flag it for plb_grid_exchange_status() and poison the result
-        reinterpret_cast<volatile uint32_t *>(mine)[2] = 1u;
-        acc.mean = __longlong_as_double(0x7ff8000000000000LL);
-    }
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {  // lane l absorbs lane l + d: ascending index order
-        Moments o;
-        o.n = __shfl_down_sync(0xffffffffu, acc.n, d);
-        o.mean = __shfl_down_sync(0xffffffffu, acc.mean, d);
-        o.m2 = __shfl_down_sync(0xffffffffu, acc.m2, d);
-        if (lane + d < 32) acc = merge(acc, o);
-    }
-    if (lane == 0) warp_scratch[warp] = acc;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        acc = warp_scratch[0];
-        for (int w = 1; w < nwarps; ++w) acc = merge(acc, warp_scratch[w]);
-    }
-    return acc;
+    if (timed_out) reinterpret_cast<volatile uint32_t *>(mine)[2] = 1u;  // no trap: plb_grid_exchange_status() reports it
+    const int any_timeout = __syncthreads_or(timed_out ? 1 : 0);
+    const Sums all = block_reduce_sums(acc, scratch);
+    Moments m = to_moments(all);
+    if (any_timeout) m.mean = __longlong_as_double(0x7ff8000000000000LL);  // poison the result
+    return m;
 }
 
 // Last CTA out advances the epoch for the next launch (off the critical path).  One thread per CTA,
@@ -523,6 +562,9 @@ __device__ __forceinline__ void gx_retire(const GridXch &g, uint32_t epoch)
     const uint32_t t = atomicAdd(hdr + 1, 1u);
     if (t == gridDim.x - 1) {
         hdr[1] = 0u;
+        // every rank's hints of this epoch have arrived (all CTAs here waited for them), and nobody can send
+        // hints of epoch + 2 before this rank has published epoch + 1, i.e. after this launch: safe to clear
+        hdr[4 + (epoch & 1u)] = 0u;
         __threadfence();
         *reinterpret_cast<volatile uint32_t *>(hdr) = epoch;
     }

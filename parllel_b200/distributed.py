@@ -75,17 +75,17 @@ class GridExchange:
     """Buffers of the resident advantage kernel's in-kernel exchange (csrc/plb_scan_shared.cuh, GridXch):
     every CTA of every rank stores its partial moments into every rank's buffer and collects all of them
     from its own -- grid barrier and all-gather in one step.  With ``group`` None (one GPU) the buffer is
-    ordinary device memory; otherwise it is symmetric memory mapped into all peers (plumbing from
+    (or ``local=True``: this GPU on its own) ordinary device memory; otherwise it is symmetric memory mapped into all peers (plumbing from
     ``torch.distributed._symmetric_memory``), and creating it is a collective.  ``ok`` is False when
     peer mapping is unavailable (the caller then keeps to the other routes)."""
 
-    def __init__(self, group=None, device=None) -> None:
+    def __init__(self, group=None, device=None, local: bool = False) -> None:
         lib = _lib.load()
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.slots = int(lib.plb_grid_exchange_slots())
         self.ok = self.slots > 0
         self.handle = None
-        single = group is None and not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1)
+        single = local or not (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1)
         if single:
             self.group, self.world, self.rank = None, 1, 0
             self.buffer = torch.zeros(lib.plb_grid_exchange_bytes(1, max(self.slots, 1)), dtype=torch.uint8, device=self.device)

@@ -24,6 +24,14 @@ class RunningMeanStdModel(nn.Module):
         self.register_buffer("var", torch.ones(self.shape, device=dev))
         self.register_buffer("count", torch.zeros((), device=dev))
 
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs) -> None:
+        """Checkpoint restore: the registered buffers are what a state dict carries (as in the reference,
+        where they ARE the state), so after loading them the float64 working statistics are rebuilt from
+        them -- otherwise the next ``update()`` would merge into fresh statistics and overwrite the restore."""
+        super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
+        self._stats.load_state(self.mean.detach().double().cpu().numpy(), self.var.detach().double().cpu().numpy(),
+                               float(self.count.item()))
+
     def update(self, x: torch.Tensor) -> None:
         """``x``: ``[T, B, *shape]``, ``[B, *shape]`` or ``[*shape]`` float32 CUDA tensor (models.py:207-209)."""
         import torch.distributed as dist

@@ -40,22 +40,18 @@ class BatchedDataLoader:
         batch_transform: Callable | None = None,
         device=None,
     ) -> None:
-        self.tree = self.source_tree = tree
-        self.batch_only_fields = batch_only_fields
+        identity = lambda tree_: tree_  # noqa: E731
+        self.source_tree = tree
+        self.tree = tree
         self.sampler_batch_spec = sampler_batch_spec
-        self.recurrent = recurrent
-        self.shuffle = shuffle
-        self.drop_last = drop_last
-        # If recurrent, use whole trajectories, only shuffle B; else shuffle all.
-        self.size = sampler_batch_spec.B if recurrent else sampler_batch_spec.size
-        self.batch_size = self.size // n_batches
+        self.batch_only_fields = batch_only_fields
+        self.recurrent, self.shuffle, self.drop_last = recurrent, shuffle, drop_last
         self.n_batches = n_batches
-        if pre_batches_transform is None:
-            pre_batches_transform = lambda x: x  # noqa: E731
-        self.pre_batches_transform = pre_batches_transform
-        if batch_transform is None:
-            batch_transform = lambda x: x  # noqa: E731
-        self.batch_transform = batch_transform
+        # unit of shuffling: one environment's whole trajectory for recurrent agents, one (t, b) sample otherwise
+        self.size = sampler_batch_spec.B if recurrent else sampler_batch_spec.T * sampler_batch_spec.B
+        self.batch_size = self.size // n_batches
+        self.pre_batches_transform = pre_batches_transform or identity
+        self.batch_transform = batch_transform or identity
         self.device = torch.device(device) if device is not None else None
         self.seed(None)
 
@@ -120,35 +116,38 @@ class BatchedDataLoader:
                        "plb_gather_tree")
         return _unflatten(zip(paths, outs))
 
+    def _pieces(self):
+        """(start, stop) of every minibatch in the permuted index list: ``n_batches`` equal pieces, plus a
+        shorter final one when the size does not divide and ``drop_last`` is off."""
+        stop_at = self.size - self.batch_size + 1 if self.drop_last else self.size
+        return [(lo, min(lo + self.batch_size, self.size)) for lo in range(0, stop_at, self.batch_size)]
+
     def batches(self) -> Iterator[ArrayDict]:
         self.tree = self.pre_batches_transform(self.source_tree)
         paths, rings, batch_only = self._device_leaves(self.tree)
         T = self.sampler_batch_spec.T
 
-        all_indices = np.arange(self.size, dtype=np.int32)
+        # the permutation is drawn exactly as the reference draws it (int32 arange, Generator.shuffle), so a
+        # seeded loader visits the samples in the reference's order; it is uploaded once per epoch
+        order = np.arange(self.size, dtype=np.int32)
         if self.shuffle:
-            self.rng.shuffle(all_indices)
-        perm = torch.from_numpy(all_indices.astype(np.int64)).to(self.device, non_blocking=True)
-        # split the data into equally-sized pieces of `batch_size`
-        if self.drop_last:
-            starts = range(0, self.size - self.batch_size + 1, self.batch_size)
-        else:
-            starts = range(0, self.size, self.batch_size)
-        for start in starts:
-            batch_indices = perm[start: min(self.size, start + self.batch_size)]
-            nb = batch_indices.numel()
+            self.rng.shuffle(order)
+        perm = torch.from_numpy(order.astype(np.int64)).to(self.device, non_blocking=True)
+        time_steps = torch.arange(T, device=self.device, dtype=torch.int64) if self.recurrent else None
+        for lo, hi in self._pieces():
+            picked = perm[lo:hi]
+            nb = hi - lo
             if self.recurrent:
-                # take entire trajectories, indexing only the B dimension: out[t, i] = leaf[t, idx[i]]
-                t_idx = torch.arange(T, device=self.device, dtype=torch.int64).repeat_interleave(nb)
-                b_idx = batch_indices.repeat(T)
+                # whole trajectories of the picked environments: out[t, i] = leaf[t, picked[i]]
+                t_idx = time_steps.repeat_interleave(nb)
+                b_idx = picked.repeat(T)
                 batch = self._gather(paths, rings, batch_only, t_idx, b_idx, (T, nb))
             else:
-                # split indices into T and B indices using modulo and remainder; T and B are flattened
-                t_idx = (batch_indices % T).contiguous()
-                b_idx = torch.div(batch_indices, T, rounding_mode="floor").contiguous()
+                # a flat sample number s addresses (t, b) = (s mod T, s div T); leading dims collapse to [nb]
+                t_idx = torch.remainder(picked, T)
+                b_idx = torch.div(picked, T, rounding_mode="floor")
                 batch = self._gather(paths, rings, batch_only, t_idx, b_idx, (nb,))
-            batch = self.batch_transform(batch)
-            yield batch
+            yield self.batch_transform(batch)
 
     def __iter__(self) -> Iterator[ArrayDict]:
         yield from self.batches()

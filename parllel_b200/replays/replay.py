@@ -59,8 +59,8 @@ class ReplayBuffer:
         device=None,
         device_rng: bool = False,
     ) -> None:
-        """Stores more than a batch's worth of samples in a circular buffer for off-policy
-        algorithms to sample from.
+        """Ring of ``size_T`` time steps x ``B`` environments in HBM that off-policy algorithms draw
+        uniform minibatches from (interface of parllel/replays/replay.py:12-52).
 
         ``device_rng=True`` draws the indices on the GPU (csrc/plb_rng.cu, bit-exact with the host
         ``numpy.random.Generator`` stream) so a minibatch needs no host->device copy at all."""
@@ -72,11 +72,11 @@ class ReplayBuffer:
         self.batch_size = replay_batch_size
         self.newest_n_samples_invalid = newest_n_samples_invalid
         self.oldest_n_samples_invalid = oldest_n_samples_invalid
-        self._cursor: int = 0  # index of next sample to write
-        self._full = False  # has the entire buffer been written to at least once?
-        if batch_transform is None:
-            batch_transform = lambda x: x  # noqa: E731
-        self.batch_transform = batch_transform
+        # ring position: `_cursor` is the row the sampler's next batch lands on, `_full` turns true at the
+        # first wrap-around (same two attributes, same meaning, as replay.py:41-42 -- tests poke them)
+        self._cursor: int = 0
+        self._full = False
+        self.batch_transform = batch_transform if batch_transform is not None else (lambda batch: batch)
         self.seed()
 
         self._paths, self._host, self._ring = [], [], []
@@ -103,9 +103,10 @@ class ReplayBuffer:
             self._ring.append(ring)
         if len(self._ring) > _lib.GATHER_MAX_LEAVES:
             raise ValueError(f"at most {_lib.GATHER_MAX_LEAVES} leaves per gather launch")
-        # pinned staging for the sampled indices (T then B), reused by every call
-        self._idx_host = None
-        self._idx_dev = None
+        # host-drawn indices travel through a small ring of pinned staging buffers; each slot carries the
+        # event of the upload that last used it, so a backlogged stream can never see a later call's indices
+        self._idx_slots: list = []
+        self._idx_next = 0
 
     def seed(self, seed: Optional[int] = None) -> None:
         self._rng = random.default_rng(seed)
@@ -145,19 +146,45 @@ class ReplayBuffer:
 
     # ------------------------------------------------------------------------------------
     def sample_indices(self, batch_size: Optional[int] = None):
-        """The reference's index math (replay.py:55-70): int64 ``(T_idxs, B_idxs)`` on the host."""
+        """Host-side draw with the reference's generator calls in the reference's order (replay.py:55-70):
+        one ``integers`` call for the time indices, then one for the environment indices; int64 arrays."""
         n = self.batch_size if batch_size is None else batch_size
+        invalid = self.oldest_n_samples_invalid + self.newest_n_samples_invalid
         if self._full:
-            # valid region for sampling wraps around: sample [0, L) then offset and wrap
-            offset = self._cursor + self.oldest_n_samples_invalid
-            valid_length = self.size_T - self.oldest_n_samples_invalid - self.newest_n_samples_invalid
-            T_idxs = self._rng.integers(0, valid_length, size=(n,))
-            T_idxs = (T_idxs + offset) % self.size_T
+            # every row is populated; the usable window starts `oldest_invalid` rows after the write position
+            # and is addressed modulo the ring length
+            first_valid = self._cursor + self.oldest_n_samples_invalid
+            T_idxs = (self._rng.integers(0, self.size_T - invalid, size=(n,)) + first_valid) % self.size_T
         else:
-            valid_length = self._cursor - self.newest_n_samples_invalid
-            T_idxs = self._rng.integers(0, valid_length, size=(n,))
+            # only rows [0, cursor) exist yet, minus the newest ones still being completed
+            T_idxs = self._rng.integers(0, self._cursor - self.newest_n_samples_invalid, size=(n,))
         B_idxs = self._rng.integers(0, self.batch_spec.B, size=(n,))
         return T_idxs, B_idxs
+
+    _IDX_SLOTS = 4
+
+    def _stage_indices(self, T_idxs, B_idxs, n: int):
+        """Upload host indices through the next pinned slot; returns the device views ``(t, b)``."""
+        dev = self.device
+        k = self._idx_next % self._IDX_SLOTS
+        self._idx_next += 1
+        if len(self._idx_slots) <= k:
+            self._idx_slots.append(None)
+        slot = self._idx_slots[k]
+        if slot is None or slot[0].shape[1] < n:
+            slot = [torch.empty((2, n), dtype=torch.int64).pin_memory(),
+                    torch.empty((2, n), dtype=torch.int64, device=dev), None]
+            self._idx_slots[k] = slot
+        host, devbuf, uploaded = slot
+        if uploaded is not None:
+            uploaded.synchronize()  # the DMA that last read this pinned slot has finished
+        host[0, :n] = torch.from_numpy(np.ascontiguousarray(T_idxs, np.int64))
+        host[1, :n] = torch.from_numpy(np.ascontiguousarray(B_idxs, np.int64))
+        devbuf[:, :n].copy_(host[:, :n], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(dev))
+        slot[2] = ev
+        return devbuf[0, :n], devbuf[1, :n]
 
     def gather(self, T_idxs, B_idxs) -> ArrayDict:
         """``self.tree[T_idxs, B_idxs]`` (replay.py:72) as one CUDA launch; indices may be host
@@ -168,13 +195,7 @@ class ReplayBuffer:
             n = t_dev.numel()
         else:
             n = len(T_idxs)
-            if self._idx_host is None or self._idx_host.shape[1] < n:
-                self._idx_host = torch.empty((2, n), dtype=torch.int64).pin_memory()
-                self._idx_dev = torch.empty((2, n), dtype=torch.int64, device=dev)
-            self._idx_host[0, :n] = torch.from_numpy(np.ascontiguousarray(T_idxs, np.int64))
-            self._idx_host[1, :n] = torch.from_numpy(np.ascontiguousarray(B_idxs, np.int64))
-            self._idx_dev[:, :n].copy_(self._idx_host[:, :n], non_blocking=True)
-            t_dev, b_dev = self._idx_dev[0, :n], self._idx_dev[1, :n]
+            t_dev, b_dev = self._stage_indices(T_idxs, B_idxs, n)
         outs = []
         leaves = (_lib.GatherLeaf * len(self._ring))()
         for k, ring in enumerate(self._ring):
@@ -227,13 +248,14 @@ class ReplayBuffer:
         yield from self.batches()
 
     def next_iteration(self) -> None:
-        # rows the sampler has just written: [cursor, cursor + T) -- refresh the HBM mirror
-        lo, hi = self._cursor, self._cursor + self.batch_spec.T
+        """The sampler has filled rows [cursor, cursor + T): bring the HBM mirror of host leaves up to date
+        (device leaves are shared with the writer and need nothing), then advance the write position."""
+        T = self.batch_spec.T
+        lo = self._cursor
         for host, ring in zip(self._host, self._ring):
             if host is not None:
-                ring[lo:hi].copy_(host[lo:hi], non_blocking=False)
-        # move cursor forward
-        self._cursor += self.batch_spec.T
-        if self._cursor >= self.size_T:
-            self._cursor %= self.size_T
+                ring[lo:lo + T].copy_(host[lo:lo + T], non_blocking=False)
+        self._cursor = lo + T
+        if self._cursor >= self.size_T:  # wrapped: from now on the whole ring holds samples
+            self._cursor -= self.size_T * (self._cursor // self.size_T)
             self._full = True

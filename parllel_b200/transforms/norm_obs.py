@@ -44,6 +44,12 @@ class NormalizeObservations(Transform):
         # EXTENSION (not in the reference): clamp the normalised observation to [-clip, clip] in the same pass
         self.clip = clip
 
+    def state_dict(self) -> dict:
+        return {"obs_statistics": self.obs_statistics.state_dict()}
+
+    def load_state_dict(self, state: dict) -> None:
+        self.obs_statistics.load_state_dict(state["obs_statistics"])
+
     def __call__(self, sample_tree):
         step_obs = sample_tree["observation"]
         assert is_array_leaf(step_obs)
@@ -73,11 +79,12 @@ class NormalizeObservations(Transform):
             x = obs.reshape(B, -1)
             ptr, ld, cols = rows_2d(x)
             stats = self.obs_statistics
-            _lib.check(_lib.load().plb_normalize_columns_f32(ptr, ld, B, cols, stats.mean_tensor.data_ptr(),
-                                                             stats.var_tensor.data_ptr(), EPSILON, stream_ptr(device)),
-                       "plb_normalize_columns_f32")
-            if self.clip is not None:
-                obs.clamp_(-float(self.clip), float(self.clip))
+            lo = _lib.NAN if self.clip is None else -float(self.clip)
+            hi = _lib.NAN if self.clip is None else float(self.clip)
+            _lib.check(_lib.load().plb_normalize_columns_clip_f32(ptr, ld, B, cols, stats.mean_tensor.data_ptr(),
+                                                                  stats.var_tensor.data_ptr(), EPSILON, lo, hi,
+                                                                  stream_ptr(device)),
+                       "plb_normalize_columns_clip_f32")
             return
         lib = _lib.load()
         B = obs.shape[0]

@@ -50,6 +50,23 @@ class NormalizeRewards(Transform):
         self._carry_done = None
         self._fused = None
 
+    # -- checkpoint / resume (the reference keeps this state in plain attributes that pickle with it) ----
+    def state_dict(self) -> dict:
+        state = {"return_statistics": self.return_statistics.state_dict()}
+        if self._carry_return is not None:
+            state["carry_return"] = self._carry_return.cpu().numpy().copy()
+        if self._carry_done is not None:
+            state["carry_done"] = self._carry_done.cpu().numpy().copy()
+        return state
+
+    def load_state_dict(self, state: dict) -> None:
+        self.return_statistics.load_state_dict(state["return_statistics"])
+        dev = self.return_statistics.device
+        if "carry_return" in state:
+            self._carry_return = torch.as_tensor(state["carry_return"], dtype=torch.float32).to(dev)
+        if "carry_done" in state:
+            self._carry_done = torch.as_tensor(state["carry_done"], dtype=torch.bool).to(dev)
+
     def __call__(self, sample_tree):
         reward_leaf = sample_tree["reward"]
         assert is_array_leaf(reward_leaf)

@@ -116,7 +116,7 @@ class FusedBatchTransforms(Transform):
         resident kernel; on one GPU a plain zeroed device buffer, on several a symmetric (peer-mapped) one."""
         if self._gx is None or self._gx.device != dev:
             from ..distributed import GridExchange
-            self._gx = GridExchange(self.group if self._distributed() else None, dev)
+            self._gx = GridExchange(self.group, dev, local=not self._distributed())
         return self._gx
 
     def _agree_plan(self, lib, d, key: bytes) -> int:

@@ -49,6 +49,13 @@ class RunningMeanStd:
         self.var_tensor.copy_(torch.as_tensor(np.asarray(var, np.float64).reshape(-1)))
         self.count_tensor.fill_(float(count))
 
+    def state_dict(self) -> dict:
+        """Checkpointable copy of the running state (numpy float64), for ``load_state_dict``."""
+        return {"mean": self.mean.copy(), "var": self.var.copy(), "count": float(self.count)}
+
+    def load_state_dict(self, state: dict) -> None:
+        self.load_state(state["mean"], state["var"], state["count"])
+
     def _workspace(self, nbytes: int) -> torch.Tensor:
         if self._ws is None or self._ws.numel() < nbytes:
             self._ws = torch.zeros(max(nbytes, 64), dtype=torch.uint8, device=self.device)
