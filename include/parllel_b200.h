@@ -79,7 +79,8 @@ PLB_API int plb_sm_count(void);
  *   key 7: slab width of observation variant 4: 8, 16 (default) or 32 columns
  *   key 9: cap on the input ring depth of the chunked scan (0 = as many stages as fit)
  *   key 11: grid cap of the streaming normalise kernels, CTAs of 256 threads per SM (default 4)
- *   key 12: 0 = never take the resident (tensor-memory) advantage kernel (default 1)
+ *   key 12: resident (tensor-memory) advantage kernel: 0 never, 1 (default) when B is sharded over several GPUs,
+ *           2 wherever the batch fits (also on one GPU)
  *   key 14 / 15: experiments on the resident kernel (1 = plain instead of cooperative launch / every thread polls)
  *   key 16: 1 = replay gather through the load/store-unit path only (default 0: TMA-staged rows of >= 128 B)
  *   key 13: 0 = index generation always by the single-CTA kernel (default 1: 8-CTA cluster kernel)

@@ -73,7 +73,7 @@ static int run_pipeline(const plb_batch_pipeline *d, int phases, cudaStream_t st
     gx.peers = reinterpret_cast<unsigned char *const *>(d->gx_peers);
     gx.rank = d->gx_rank; gx.world = d->gx_world; gx.slots = d->gx_slots;
     const bool want_resident = est_adv && norm_adv && (phases & PLB_PHASE_B) && (phases & PLB_PHASE_C) && !split_partials &&
-                               gx.peers != nullptr && (plan & PLB_PLAN_RESIDENT) &&
+                               gx.peers != nullptr && (plan & PLB_PLAN_RESIDENT) && resident_wanted(gx.world) &&
                                (gx.world > 1 ? plan != PLB_PLAN_AUTO : true);
     const bool update_in_tail = (phases == PLB_PHASE_ALL) && norm_rew && !use_xch;
     bool state_updated = false;
@@ -254,7 +254,7 @@ static int pipeline_plan(const plb_batch_pipeline *d)
     const bool adv_vec = !d->normalize_advantage ||
                          (aligned(d->advantage, 16) && d->ld_advantage % 4 == 0 && (d->ld_advantage == d->B ? (d->T * d->B) % 4 == 0 : d->B % 4 == 0));
     if (fwd_ok && rev_ok && adv_vec) plan |= PLB_PLAN_CHUNKED;
-    if (d->estimate_advantage && d->normalize_advantage && rev_ok &&
+    if (d->estimate_advantage && d->normalize_advantage && rev_ok && resident_wanted(d->gx_world > 1 ? d->gx_world : 2) &&
         resident_supported(d->reward, d->ld_reward, d->value, d->ld_value, d->done, d->ld_done, d->advantage, d->ld_advantage,
                            d->return_, d->ld_return, d->T, d->B))
         plan |= PLB_PLAN_RESIDENT;

@@ -100,6 +100,7 @@ struct ScanFusion {
 };
 bool scan_chunked_supported(const float *reward, int64_t ld_r, const float *value, int64_t ld_v,
                             const uint8_t *done, int64_t ld_d, int64_t T, int64_t B, int64_t inner);
+bool resident_wanted(int world);  // policy (plb_set_tuning key 12)
 bool resident_supported(const float *reward, int64_t ld_r, const float *value, int64_t ld_v, const uint8_t *done,
                         int64_t ld_d, const float *adv, int64_t ld_a, const float *ret, int64_t ld_t,
                         int64_t T, int64_t B);
@@ -224,6 +225,21 @@ template <int N>
 __device__ __forceinline__ void tma_store_wait_read()
 {
     asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+// at most `n` of this thread's bulk groups may still be reading shared memory (n clamped to [0, 8])
+__device__ __forceinline__ void tma_store_wait_read_dyn(int n)
+{
+    switch (n) {
+        case 0: tma_store_wait_read<0>(); break;
+        case 1: tma_store_wait_read<1>(); break;
+        case 2: tma_store_wait_read<2>(); break;
+        case 3: tma_store_wait_read<3>(); break;
+        case 4: tma_store_wait_read<4>(); break;
+        case 5: tma_store_wait_read<5>(); break;
+        case 6: tma_store_wait_read<6>(); break;
+        case 7: tma_store_wait_read<7>(); break;
+        default: tma_store_wait_read<8>(); break;
+    }
 }
 template <int N>
 __device__ __forceinline__ void tma_store_wait()
@@ -379,7 +395,26 @@ __device__ __forceinline__ void tmem_st(uint32_t taddr, const float (&x)[N])
                      : "memory");
     }
 }
+// wait::ld that also "touches" the destination registers, so that no use of them can be scheduled above it
 template <int N>
+__device__ __forceinline__ void tmem_wait_ld_regs(float (&x)[N])
+{
+    static_assert(N == 8 || N == 16, "8 or 16 registers");
+    if constexpr (N == 16) {
+        asm volatile("tcgen05.wait::ld.sync.aligned;"
+                     : "+f"(x[0]), "+f"(x[1]), "+f"(x[2]), "+f"(x[3]), "+f"(x[4]), "+f"(x[5]), "+f"(x[6]), "+f"(x[7]),
+                       "+f"(x[8]), "+f"(x[9]), "+f"(x[10]), "+f"(x[11]), "+f"(x[12]), "+f"(x[13]), "+f"(x[14]), "+f"(x[15])
+                     :
+                     : "memory");
+    } else {
+        asm volatile("tcgen05.wait::ld.sync.aligned;"
+                     : "+f"(x[0]), "+f"(x[1]), "+f"(x[2]), "+f"(x[3]), "+f"(x[4]), "+f"(x[5]), "+f"(x[6]), "+f"(x[7])
+                     :
+                     : "memory");
+    }
+}
+// WAIT = false: the caller overlaps the load with other work and calls tmem_wait_ld_regs(x) before reading x
+template <int N, bool WAIT = true>
 __device__ __forceinline__ void tmem_ld(uint32_t taddr, float (&x)[N])
 {
     static_assert(N == 8 || N == 16, "tmem_ld: 8 or 16 columns");
@@ -395,7 +430,7 @@ __device__ __forceinline__ void tmem_ld(uint32_t taddr, float (&x)[N])
                      : "r"(taddr)
                      : "memory");
     }
-    tmem_wait_ld();
+    if (WAIT) tmem_wait_ld_regs<N>(x);
 }
 
 // x / d through the correctly rounded reciprocal r = 1/d and one FMA residual step (Markstein): the IEEE

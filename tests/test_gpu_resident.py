@@ -13,6 +13,17 @@ from tests.util import assert_within_tolerance, make_batch
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True)
+def _resident_on_one_gpu():
+    """The library's default policy takes the resident kernel only when B is sharded over several GPUs (on one
+    GPU the two-kernel route is faster); these tests force it on the single GPU they run on."""
+    from parllel_b200 import _lib
+    lib = _lib.load()
+    lib.plb_set_tuning(12, 2)
+    yield
+    lib.plb_set_tuning(12, 1)
+
+
 def _tree(batch, dev="cuda", extra=()):
     from parllel_b200 import ArrayDict
     t = {k: torch.from_numpy(v).to(dev) for k, v in batch.items()}
@@ -76,7 +87,7 @@ def test_resident_equals_two_kernel_route(T, B):
         _fused(b, 0.95)(b)
         assert _lib.launch_counters()[1] == before[1], "resident kernel ran although switched off"
     finally:
-        lib.plb_set_tuning(12, 1)
+        lib.plb_set_tuning(12, 2)
     assert torch.equal(a["return_"], b["return_"])
     np.testing.assert_allclose(a["advantage"].cpu().numpy(), b["advantage"].cpu().numpy(), rtol=3e-7, atol=3e-7)
 
@@ -171,6 +182,19 @@ def test_full_chain_with_resident_tail_vs_oracle():
     O.normalize_advantage(adv)
     for k, ref in (("past_return", past), ("reward", r), ("return_", ret), ("advantage", adv)):
         assert_within_tolerance(tree[k].cpu().numpy(), ref, what=f"chain {k}")
+
+
+def test_default_policy_keeps_one_gpu_on_the_two_kernel_route():
+    from parllel_b200 import _lib
+    _lib.load().plb_set_tuning(12, 1)
+    batch = make_batch(np.random.default_rng(4), 128, 256, 0.01)
+    adv_ref, ret_ref = _oracle_step(batch, 0.99, 0.95)
+    tree = _tree(batch)
+    before = _lib.launch_counters()
+    _fused(tree, 0.95)(tree)
+    after = _lib.launch_counters()
+    assert after[1] == before[1] and after[0] - before[0] == 2
+    assert_within_tolerance(tree["advantage"].cpu().numpy(), adv_ref, what="advantage")
 
 
 def test_batches_too_large_for_tensor_memory_take_the_two_kernel_route():

@@ -59,7 +59,7 @@ def main():
     ap.add_argument("--n", type=int, default=16384)
     ap.add_argument("--inner", type=int, default=1, help="launches per event pair (rotating buffer sets)")
     ap.add_argument("--rows", type=int, default=0)
-    ap.add_argument("--resident", type=int, default=1, help="0: never take the resident (tensor-memory) advantage kernel")
+    ap.add_argument("--resident", type=int, default=1, help="resident advantage kernel: 0 never, 1 auto (multi-GPU only), 2 wherever it fits")
     ap.add_argument("--stages", type=int, default=0, help="cap on the input ring depth (0 = as many as fit)")
     ap.add_argument("--obs-variant", type=int, default=0)
     ap.add_argument("--debug", type=int, default=0)
