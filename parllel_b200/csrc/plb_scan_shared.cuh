@@ -24,34 +24,6 @@ struct XchRef {
 };
 constexpr size_t XCH_HEADER_BYTES = 1024;  // uint32 epoch @0, uint32 flags[2][world] @64, data @1024
 
-struct MomentsTail {
-    double *moments_out;  // [3] = (count, mean, M2); nullptr disables the tail
-    Sums *partials;
-    unsigned *ticket;     // workspace word 0: last-CTA ticket; word 1: number of partials written
-    int partials_only;    // 1: every CTA only publishes its partial Sums (and the CTA count); the
-                          //    consumer kernel reduces them itself (no serial last-CTA epilogue)
-    // optional: the CTA that finishes the reduction also folds the batch moments into a scalar
-    // running state (update_from_moments, running_mean_std.py:7-32) -- saves a kernel launch
-    double *upd_mean, *upd_var, *upd_count;
-    int upd_flags;
-    // optional (multi-GPU): the finishing CTA pushes the final moments straight into every peer's
-    // exchange buffer (NVLink P2P stores + release flags); the consumer kernel waits and merges
-    XchRef xch;
-};
-
-static inline MomentsTail make_tail(double *moments_out, void *workspace)
-{
-    MomentsTail t;
-    t.moments_out = moments_out;
-    t.ticket = reinterpret_cast<unsigned *>(workspace);
-    t.partials = reinterpret_cast<Sums *>(reinterpret_cast<unsigned char *>(workspace) + 64);
-    t.partials_only = 0;
-    t.upd_mean = t.upd_var = t.upd_count = nullptr;
-    t.upd_flags = 0;
-    t.xch.peers = nullptr; t.xch.rank = 0; t.xch.world = 1;
-    return t;
-}
-
 // Grid-wide + cross-GPU statistics exchange of the resident advantage kernel (one protocol for both):
 // every CTA of every rank stores its partial (count, mean, M2) as an epoch-tagged record straight into
 // EVERY rank's buffer (its own included; NVLink P2P stores for the peers), then polls its own rank's
@@ -59,6 +31,8 @@ static inline MomentsTail make_tail(double *moments_out, void *workspace)
 // order -- so the grid barrier of one GPU and the all-gather across GPUs are the same step, with no
 // atomics, no last-CTA reduction and no second kernel.  Buffer layout (plb_grid_exchange_bytes):
 //     uint32 epoch @0 | uint32 exit_ticket @4 | uint32 status @8 (0 ok, 1 timed out)
+//     uint4 result[2] @32 (by epoch parity): {mean, epoch, denominator, epoch} left by the collector CTA of the
+//            two-kernel route for the other CTAs of its grid (local to the rank)
 //     uint32 arrived[2] @16 (by epoch parity): slots filled so far, a HINT for when to read -- the
 //            records validate themselves through their epoch tags, so no fence orders it after them
 //     records @256: [2 (epoch parity)][world][slots] x 64 B = 4 x {lo, epoch, hi, epoch} 16-byte units
@@ -76,6 +50,38 @@ constexpr int GX_MAX_SLOTS = 1024;
 __host__ __device__ __forceinline__ size_t gx_total_bytes(int world, int slots)
 {
     return GX_HEADER_BYTES + 2 * (size_t)world * (size_t)slots * GX_RECORD_BYTES;
+}
+
+struct MomentsTail {
+    double *moments_out;  // [3] = (count, mean, M2); nullptr disables the tail
+    Sums *partials;
+    unsigned *ticket;     // workspace word 0: last-CTA ticket; word 1: number of partials written
+    int partials_only;    // 1: every CTA only publishes its partial Sums (and the CTA count); the
+                          //    consumer kernel reduces them itself (no serial last-CTA epilogue)
+    // optional: the CTA that finishes the reduction also folds the batch moments into a scalar
+    // running state (update_from_moments, running_mean_std.py:7-32) -- saves a kernel launch
+    double *upd_mean, *upd_var, *upd_count;
+    int upd_flags;
+    // optional (multi-GPU): the finishing CTA pushes the final moments straight into every peer's
+    // exchange buffer (NVLink P2P stores + release flags); the consumer kernel waits and merges
+    XchRef xch;
+    // optional: instead of any local reduction, every CTA publishes its partial sums into the grid-exchange
+    // records of every rank (gx_publish); the consumer kernel collects them (normalize_advantage_after_gx)
+    GridXch gx;
+};
+
+static inline MomentsTail make_tail(double *moments_out, void *workspace)
+{
+    MomentsTail t;
+    t.moments_out = moments_out;
+    t.ticket = reinterpret_cast<unsigned *>(workspace);
+    t.partials = reinterpret_cast<Sums *>(reinterpret_cast<unsigned char *>(workspace) + 64);
+    t.partials_only = 0;
+    t.upd_mean = t.upd_var = t.upd_count = nullptr;
+    t.upd_flags = 0;
+    t.xch.peers = nullptr; t.xch.rank = 0; t.xch.world = 1;
+    t.gx.peers = nullptr; t.gx.rank = 0; t.gx.world = 1; t.gx.slots = 0;
+    return t;
 }
 
 // Optional work fused into the chunked scans (host-side description).
@@ -101,6 +107,7 @@ struct ScanFusion {
 bool scan_chunked_supported(const float *reward, int64_t ld_r, const float *value, int64_t ld_v,
                             const uint8_t *done, int64_t ld_d, int64_t T, int64_t B, int64_t inner);
 bool resident_wanted(int world);  // policy (plb_set_tuning key 12)
+int sharded_route();              // plb_set_tuning key 17
 bool resident_supported(const float *reward, int64_t ld_r, const float *value, int64_t ld_v, const uint8_t *done,
                         int64_t ld_d, const float *adv, int64_t ld_a, const float *ret, int64_t ld_t,
                         int64_t T, int64_t B);
@@ -142,6 +149,8 @@ int exchange_finish(const XchRef &xch, double *moments_out, double *upd_mean, do
                     int upd_flags, cudaStream_t stream);
 int normalize_advantage_after_exchange(float *x, int64_t ld_x, int64_t rows, int64_t cols, const XchRef &xch, double eps,
                                        double *moments_out, cudaStream_t stream);
+int normalize_advantage_after_gx(float *x, int64_t ld_x, int64_t rows, int64_t cols, const GridXch &gx, double eps,
+                                 double *moments_out, cudaStream_t stream);
 int normalize_advantage_from_partials(float *x, int64_t ld_x, int64_t rows, int64_t cols, void *tail_workspace,
                                       double eps, double *moments_out, cudaStream_t stream);
 int make_tensor_map_2d(CUtensorMap *tm, const void *base, int elem_bytes, int64_t rows, int64_t cols,
@@ -644,6 +653,17 @@ __device__ __forceinline__ void moments_tail(const Sums &mine, const MomentsTail
     __shared__ bool is_last;
     __syncthreads();  // scratch may have been used before
     const Sums blk = WARP_PIVOT ? block_reduce_sums_warp_pivot(mine, scratch) : block_reduce_sums(mine, scratch);
+    if (tail.gx.peers != nullptr) {
+        __shared__ double s_gx_pub[GX_RECORD_VALS];
+        __shared__ uint32_t s_gx_epoch;
+        if (threadIdx.x == 0) {
+            s_gx_pub[0] = blk.n; s_gx_pub[1] = blk.s1; s_gx_pub[2] = blk.s2; s_gx_pub[3] = blk.piv;
+            s_gx_epoch = gx_epoch(tail.gx);  // stays put until the CONSUMER kernel's last CTA retires the epoch
+        }
+        __syncthreads();
+        gx_publish(tail.gx, s_gx_epoch, s_gx_pub);
+        return;
+    }
     if (tail.partials_only) {
         if (threadIdx.x == 0) {
             tail.partials[blockIdx.x] = blk;

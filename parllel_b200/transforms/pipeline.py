@@ -245,26 +245,22 @@ class FusedBatchTransforms(Transform):
         if distributed:
             d.plan = 0
             d.plan = self._agree_plan(lib, d, bytes(d) + bytes([phases]))
-        resident_ready = False
+        # grid-exchange buffers: the resident kernel (one GPU when forced, or sharded) and the sharded two-kernel
+        # route both trade their partial sums through them
         if phases == _lib.PHASE_ALL and (not st.staged or not distributed) and est is not None and na is not None \
-                and (d.plan & _lib.PLAN_RESIDENT) and os.environ.get("PLB_EXCHANGE", "p2p") == "p2p":
+                and (d.plan & (_lib.PLAN_RESIDENT | _lib.PLAN_CHUNKED)) and os.environ.get("PLB_EXCHANGE", "p2p") == "p2p":
             gx = self._grid_exchange(dev)
             if gx.ok:
                 d.gx_peers, d.gx_rank, d.gx_world, d.gx_slots = gx.peer_table.data_ptr(), gx.rank, gx.world, gx.slots
                 keep.append(gx)
-                resident_ready = True
-        if distributed and not resident_ready:
-            d.plan &= ~_lib.PLAN_RESIDENT
-        if distributed and phases == _lib.PHASE_ALL and not st.staged:
-            if nr is None and resident_ready:
-                in_kernel_exchange = True  # the only statistic of this chain travels inside the resident kernel
-            elif d.plan & _lib.PLAN_CHUNKED:
-                from ..distributed import get_peer_exchange
-                ex = get_peer_exchange(3, self.group, dev)
-                if ex is not None and ex.world <= 32:
-                    d.xch_peers, d.xch_rank, d.xch_world = ex.peer_table.data_ptr(), ex.rank, ex.world
-                    keep.append(ex)
-                    in_kernel_exchange = True
+        if distributed and phases == _lib.PHASE_ALL and not st.staged and (d.plan & _lib.PLAN_CHUNKED):
+            # the round-1 record-per-rank buffers: NormalizeRewards' statistics, and the fallback route
+            from ..distributed import get_peer_exchange
+            ex = get_peer_exchange(3, self.group, dev)
+            if ex is not None and ex.world <= 32:
+                d.xch_peers, d.xch_rank, d.xch_world = ex.peer_table.data_ptr(), ex.rank, ex.world
+                keep.append(ex)
+                in_kernel_exchange = True
 
         def enqueue():
             s = stream_ptr(dev)

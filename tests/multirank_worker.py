@@ -1,7 +1,7 @@
 """Multi-GPU parity worker (one process per GPU under torchrun; driven by tests/test_gpu_multirank.py):
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
-        --master-port P tests/multirank_worker.py [--log gpurun_out/multirank_wN.json]
+        --master-port P tests/multirank_worker.py      (PLB_MULTIRANK_LOG=gpurun_out/multirank_wN.json keeps the report)
 
 Every rank builds the SAME global batch from a seed, keeps its contiguous block of env columns
 (parllel_b200.distributed.column_shard) and runs the sharded transforms.  Checked on every rank:
@@ -72,8 +72,9 @@ def identical_across_ranks(t, world):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--log", default="")
+    ap.add_argument("--report", default=os.environ.get("PLB_MULTIRANK_LOG", ""))
     args = ap.parse_args()
+    args.log = args.report
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -93,9 +94,11 @@ def main():
         if rank == 0:
             print(f"[multirank w{world}] {name}: {kw}", flush=True)
 
-    # ---- 1. C4-shaped step (EstimateAdvantage + NormalizeAdvantage), lambda 0.95 and 1.0 --------------
+    # ---- 1. C4-shaped step (EstimateAdvantage + NormalizeAdvantage): every exchange route, lambda 0.95 and 1.0 ----
     T, B = 256, 65536
-    for lam in (0.95, 1.0):
+    routes = {2: "two kernels + grid exchange (default)", 1: "resident kernel", 3: "last-CTA reduction + record per rank"}
+    for lam, route in ((0.95, 2), (0.95, 1), (0.95, 3), (1.0, 2), (1.0, 1)):
+        _lib.load().plb_set_tuning(17, route)
         g = synth(2, T, B)
         adv, ret = np.empty_like(g["value"]), np.empty_like(g["value"])
         fn = O.compute_discount_return if lam == 1.0 else O.compute_gae_advantage
@@ -106,11 +109,11 @@ def main():
         tree = shard_tree(g, sl, dev, chain=False)
         fused = FusedBatchTransforms([EstimateAdvantage(GAMMA, lam), NormalizeAdvantage(tree)])
         before = _lib.launch_counters()
-        for _ in range(3):  # eager, captured, replayed: same inputs, outputs overwritten each time
+        for _ in range(4):  # eager, captured, replayed twice: same inputs, outputs overwritten each time
             tree["advantage"].fill_(float("nan"))
             fused(tree)
         torch.cuda.synchronize()
-        resident = _lib.launch_counters()[1] - before[1]
+        after = _lib.launch_counters()
         v = {"advantage": max_violation(tree["advantage"].cpu().numpy(), adv[:, sl]),
              "return_": max_violation(tree["return_"].cpu().numpy(), ret[:, sl])}
         same = identical_across_ranks(fused._moments, world)
@@ -126,8 +129,10 @@ def main():
         v["advantage_nccl"] = max_violation(tree2["advantage"].cpu().numpy(), adv[:, sl])
         np.testing.assert_allclose(tree["advantage"].cpu().numpy(), tree2["advantage"].cpu().numpy(), rtol=3e-7, atol=3e-7)
         os.environ["PLB_EXCHANGE"] = "p2p"
-        record(f"C4 step lambda={lam}", T=T, B_total=B, resident_launches=resident, stats_identical=same, violations=v)
+        record(f"C4 step lambda={lam} route={routes[route]}", T=T, B_total=B, kernels_enqueued=after[0] - before[0],
+               resident_launches=after[1] - before[1], stats_identical=same, violations=v)
         del tree, tree2, fused, fused2
+    _lib.load().plb_set_tuning(17, 0)
 
     # ---- 2. the four-transform chain over three consecutive batches (state carried between them) -------
     T, B = 256, 1024 * world

@@ -28,8 +28,8 @@ def test_sharded_transforms_match_the_oracle_on_the_global_batch(world):
     log = os.path.join(ROOT, "gpurun_out", f"multirank_w{world}.json")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
-           os.path.join(ROOT, "tests", "multirank_worker.py"), "--log", log]
-    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+           os.path.join(ROOT, "tests", "multirank_worker.py")]
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", PLB_MULTIRANK_LOG=log)
     proc = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
     tail = (proc.stdout + proc.stderr)[-6000:]
     assert proc.returncode == 0, tail
