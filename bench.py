@@ -142,6 +142,26 @@ class ClockSampler:
                 "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+def bind_to_gpu_numa(index: int):
+    """Pin this process (and the pinned buffers it allocates afterwards) to the CPUs NVML reports as local to
+    GPU `index`: with several ranks per box, host threads and staging memory on the far socket halve the
+    PCIe rate.  Returns the number of CPUs bound to, or None when the affinity is unknown."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+        n_cpus = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (n_cpus + 63) // 64)
+        cpus = {64 * w + b for w, mask in enumerate(words) for b in range(64) if (int(mask) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 # ----------------------------------------------------------------------------- CPU arms
 def cpu_port_arm(steps: int, warmup: int, budget_s: float, threads: int, n_shards: int = 1):
     """The oracle's C restatement of the reference algorithm on host cores (column blocks over a thread
@@ -498,6 +518,7 @@ def main():
     from parllel_b200.transforms import EstimateAdvantage, FusedBatchTransforms, NormalizeAdvantage
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device"
+    numa_cpus = bind_to_gpu_numa(local_rank) if world > 1 else None
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     distributed = world > 1
@@ -694,6 +715,8 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
                 "single_batch_latency_ms": statistics.median(lat) * 1e3,
+                "per_rank_h2d_GBs": h2d / (e2e_ms / e2e_steps * 1e-3) / 1e9, "per_rank_d2h_GBs": d2h / (e2e_ms / e2e_steps * 1e-3) / 1e9,
+                "cpus_bound_per_rank": numa_cpus,
                 "note": "value is PIPELINED throughput (batch i+1 uploads while i computes and i-1 downloads); an RL iteration "
                         "that holds one batch sees single_batch_latency_ms",
                 "api": "HostBatchPipeline(FusedBatchTransforms([EstimateAdvantage, NormalizeAdvantage])).submit(tree)/wait() on pinned numpy trees, 2 slots"},

@@ -345,6 +345,7 @@ typedef struct {
      * every CTA of every rank exchanges its partial moments through these buffers, and is written once,
      * normalised.  `gx_slots` = records per rank (plb_grid_exchange_slots(), identical on all ranks). */
     void *const *gx_peers; int32_t gx_rank, gx_world, gx_slots;
+    void *gx_self;                                   /* this rank's buffer, i.e. gx_peers[gx_rank] (saves the kernels a dependent load) */
     /* which fused routes the call may take: PLB_PLAN_AUTO on one GPU; on several GPUs the bitwise AND over
      * all ranks of plb_batch_pipeline_plan(), so that every rank takes the same exchange protocol */
     int32_t plan;

@@ -52,6 +52,7 @@ class BatchPipeline(ctypes.Structure):
         ("xch_peers", c_void_p), ("xch_rank", c_int32), ("xch_world", c_int32),
         ("carry_return_out", c_void_p), ("carry_done_out", c_void_p),
         ("gx_peers", c_void_p), ("gx_rank", c_int32), ("gx_world", c_int32), ("gx_slots", c_int32),
+        ("gx_self", c_void_p),
         ("plan", c_int32),
     ]
 

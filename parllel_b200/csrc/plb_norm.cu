@@ -297,7 +297,7 @@ normalize_advantage_gx_kernel(float *__restrict__ x, int64_t ld_x, int64_t rows,
         }
     }
     const uint32_t epoch = gx_epoch(gx);
-    unsigned char *mine = gx.peers[gx.rank];
+    unsigned char *mine = gx.self;
     uint4 *result = reinterpret_cast<uint4 *>(mine + 32) + (epoch & 1u);  // {mean bits, epoch, denom bits, epoch}
     if (blockIdx.x == 0) {
         if (threadIdx.x == 0) gx_wait_arrivals(gx, epoch);

@@ -71,7 +71,9 @@ static int run_pipeline(const plb_batch_pipeline *d, int phases, cudaStream_t st
     const int plan = d->plan;
     GridXch gx;
     gx.peers = reinterpret_cast<unsigned char *const *>(d->gx_peers);
+    gx.self = reinterpret_cast<unsigned char *>(d->gx_self);
     gx.rank = d->gx_rank; gx.world = d->gx_world; gx.slots = d->gx_slots;
+    PLB_REQUIRE(gx.peers == nullptr || gx.self != nullptr, PLB_ERR_INVALID_ARGUMENT, "gx_peers without gx_self");
     // sharded batches (gx.world > 1) have three routes for EstimateAdvantage + NormalizeAdvantage (key 17):
     //   2 (auto)  two kernels + grid exchange: the scan's CTAs publish their partial sums to every rank as they
     //             retire, the normalise kernel's collector CTA adds them up while the other CTAs' loads are in flight;
@@ -82,8 +84,9 @@ static int run_pipeline(const plb_batch_pipeline *d, int phases, cudaStream_t st
     const bool both_phases = est_adv && norm_adv && (phases & PLB_PHASE_B) && (phases & PLB_PHASE_C) && !split_partials;
     const bool want_resident = both_phases && gx.peers != nullptr && (plan & PLB_PLAN_RESIDENT) &&
                                (multi ? (route == 1 && plan != PLB_PLAN_AUTO) : resident_wanted(1));
-    const bool want_gx2 = both_phases && multi && phases == PLB_PHASE_ALL && route == 2 && plan != PLB_PLAN_AUTO &&
-                          (plan & PLB_PLAN_CHUNKED);
+    const bool want_gx2 = both_phases && phases == PLB_PHASE_ALL && gx.peers != nullptr && (plan & PLB_PLAN_CHUNKED) &&
+                          ((multi && route == 2 && plan != PLB_PLAN_AUTO) ||
+                           (!multi && sharded_route() == 2 && !want_resident));  // one GPU: only when asked for (experiments)
     bool adv_gx_published = false;
     // a sharded single-call chain must exchange the advantage statistics one way or another
     PLB_REQUIRE(!(both_phases && phases == PLB_PHASE_ALL && (multi || (d->xch_peers != nullptr && d->xch_world > 1))) ||

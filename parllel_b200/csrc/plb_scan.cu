@@ -288,6 +288,8 @@ scan_pipelined_kernel(const __grid_constant__ TensorMaps tm, const Params p)
     const int64_t T = p.T;
 
     __shared__ uint32_t s_tmem_base, s_epoch;
+    __shared__ unsigned char *s_peers[GX_MAX_WORLD];
+    if (RESIDENT) gx_preload_peers(p.gx, s_peers);
     if (RESIDENT && p.dbg != nullptr && threadIdx.x == 0) p.dbg[blockIdx.x * 8 + 0] = global_timer_ns();
     if (threadIdx.x == 0) {
         for (int s = 0; s < n_stages; ++s) mbar_init(&sh->full[s], 1);
@@ -607,7 +609,7 @@ scan_pipelined_kernel(const __grid_constant__ TensorMaps tm, const Params p)
         const Sums blk = block_reduce_sums_warp_pivot(acc, red_scratch);
         if (threadIdx.x == 0) { s_pub[0] = blk.n; s_pub[1] = blk.s1; s_pub[2] = blk.s2; s_pub[3] = blk.piv; }
         __syncthreads();
-        gx_publish(p.gx, epoch, s_pub);
+        gx_publish(p.gx, epoch, s_pub, s_peers);
         if (p.dbg != nullptr && threadIdx.x == 0) p.dbg[blockIdx.x * 8 + 2] = global_timer_ns();
         // one thread waits for the arrival hint (cheap to poll), then everybody reads its records in one batch
         if (p.poll_mode == 0 && threadIdx.x == 0) gx_wait_arrivals(p.gx, epoch);
@@ -1007,7 +1009,7 @@ static int launch_resident(const ChunkedIO &io, chunked::Params p, bool has_pre,
     ResidentGeometry geo;
     PLB_REQUIRE(resident_geometry(p.T, p.B, sms, &geo), PLB_ERR_UNSUPPORTED,
                 "resident scan: the advantage of this batch does not fit in tensor memory");
-    PLB_REQUIRE(p.gx.peers != nullptr && p.gx.world >= 1 && p.gx.world <= GX_MAX_WORLD && p.gx.rank >= 0 &&
+    PLB_REQUIRE(p.gx.peers != nullptr && p.gx.self != nullptr && p.gx.world >= 1 && p.gx.world <= GX_MAX_WORLD && p.gx.rank >= 0 &&
                     p.gx.rank < p.gx.world && p.gx.slots >= geo.grid && p.gx.slots <= GX_MAX_SLOTS,
                 PLB_ERR_INVALID_ARGUMENT, "resident scan: bad grid-exchange description (world %d, slots %d, grid %d)",
                 p.gx.world, p.gx.slots, geo.grid);

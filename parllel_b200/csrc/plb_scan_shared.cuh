@@ -39,6 +39,7 @@ constexpr size_t XCH_HEADER_BYTES = 1024;  // uint32 epoch @0, uint32 flags[2][w
 //            carrying the division-free Sums (n, s1, s2, pivot) of one CTA
 struct GridXch {
     unsigned char *const *peers;  // device array [world]: every rank's buffer (world == 1: just ours)
+    unsigned char *self;          // this rank's buffer (= peers[rank], passed by value: no dependent table load)
     int rank, world;
     int slots;                    // records per rank and epoch (>= the largest grid of any rank)
 };
@@ -80,7 +81,7 @@ static inline MomentsTail make_tail(double *moments_out, void *workspace)
     t.upd_mean = t.upd_var = t.upd_count = nullptr;
     t.upd_flags = 0;
     t.xch.peers = nullptr; t.xch.rank = 0; t.xch.world = 1;
-    t.gx.peers = nullptr; t.gx.rank = 0; t.gx.world = 1; t.gx.slots = 0;
+    t.gx.peers = nullptr; t.gx.self = nullptr; t.gx.rank = 0; t.gx.world = 1; t.gx.slots = 0;
     return t;
 }
 
@@ -170,11 +171,6 @@ __device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t coun
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
 
-__device__ __forceinline__ void fence_mbar_init()
-{
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-
 __device__ __forceinline__ void fence_proxy_async_smem()
 {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -191,6 +187,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t pari
     const uint32_t addr = smem_u32(bar);
     uint32_t done = 0;
     unsigned spins = 0;
+    const long long t_start = clock64();
     while (true) {
         asm volatile(
             "{\n\t"
@@ -202,7 +199,8 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t pari
             : "r"(addr), "r"(parity)
             : "memory");
         if (done) break;
-        if (++spins > (1u << 24)) __trap();  // a lost TMA would otherwise hang the GPU
+        // a lost TMA would otherwise hang the GPU: give up after ~10 s of polling (checked every 2^20 polls)
+        if ((++spins & ((1u << 20) - 1u)) == 0u && clock64() - t_start > 20000000000LL) __trap();
     }
 }
 
@@ -285,11 +283,12 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p)
     return v;
 }
 
-// In-kernel exchange of one (count, mean, M2) triple per rank, low-latency ("LL") protocol: every
-// 32-bit half of the payload travels in its own naturally aligned 8-byte store {half, epoch}, so the
-// epoch tag doubles as the arrival flag -- no fence between data and flag, one NVLink store latency
-// end to end.  LL area of a rank's buffer (after the generic area of plb_exchange.cu):
-//     uint2 ll[2 (parity)][world][6]     (6 = 3 doubles x 2 halves)
+// In-kernel exchange of one record of partial sums per rank, low-latency ("LL") protocol: every 32-bit half of
+// the payload travels in its own naturally aligned 8-byte store {half, epoch}, so the epoch tag doubles as the
+// arrival flag -- no fence between data and flag, one NVLink store latency end to end.  The payload is the
+// division-free Sums (n, s1, s2, pivot), so the consumer adds the ranks up with rebase + add and divides once.
+// LL area of a rank's buffer (after the generic area of plb_exchange.cu):
+//     uint2 ll[2 (parity)][world][8]     (8 = 4 doubles x 2 halves)
 __host__ __device__ __forceinline__ size_t xch_ll_offset(int world)
 {
     const size_t generic = XCH_HEADER_BYTES + 2 * (size_t)world * 3 * sizeof(double);
@@ -297,12 +296,11 @@ __host__ __device__ __forceinline__ size_t xch_ll_offset(int world)
 }
 __host__ __device__ __forceinline__ size_t xch_total_bytes3(int world)
 {
-    return xch_ll_offset(world) + 2 * (size_t)world * 6 * 8;
+    return xch_ll_offset(world) + 2 * (size_t)world * 8 * 8;
 }
 
-// Push this rank's (count, mean, M2) to every rank.  Called by ONE full warp (world <= 32); lane 0
-// supplies the moments.
-__device__ __forceinline__ void xch_push3(const XchRef &x, double n, double mean, double m2)
+// Push this rank's sums to every rank.  Called by ONE full warp (world <= 32); lane 0 supplies them.
+__device__ __forceinline__ void xch_push3(const XchRef &x, Sums mine_sums)
 {
     const int lane = threadIdx.x & 31;
     unsigned char *mine = x.peers[x.rank];
@@ -313,60 +311,73 @@ __device__ __forceinline__ void xch_push3(const XchRef &x, double n, double mean
         *ep = epoch;
     }
     epoch = __shfl_sync(0xffffffffu, epoch, 0);
-    n = __shfl_sync(0xffffffffu, n, 0);
-    mean = __shfl_sync(0xffffffffu, mean, 0);
-    m2 = __shfl_sync(0xffffffffu, m2, 0);
+    double vals[4] = {mine_sums.n, mine_sums.s1, mine_sums.s2, mine_sums.piv};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) vals[i] = __shfl_sync(0xffffffffu, vals[i], 0);
     const int par = (int)(epoch & 1u);
     if (lane < x.world) {
         uint2 *dst = reinterpret_cast<uint2 *>(x.peers[lane] + xch_ll_offset(x.world)) +
-                     ((size_t)par * x.world + x.rank) * 6;
-        const double vals[3] = {n, mean, m2};
+                     ((size_t)par * x.world + x.rank) * 8;
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
+        for (int i = 0; i < 4; ++i) {
             const unsigned long long bits = (unsigned long long)__double_as_longlong(vals[i]);
-            uint4 pkt;  // two 8-byte units {lo, epoch} {hi, epoch} in one 16-byte store
-            pkt.x = (uint32_t)bits; pkt.y = epoch; pkt.z = (uint32_t)(bits >> 32); pkt.w = epoch;
             asm volatile("st.relaxed.sys.global.v4.u32 [%0], {%1, %2, %3, %4};"
-                         ::"l"(dst + 2 * i), "r"(pkt.x), "r"(pkt.y), "r"(pkt.z), "r"(pkt.w) : "memory");
+                         ::"l"(dst + 2 * i), "r"((uint32_t)bits), "r"(epoch), "r"((uint32_t)(bits >> 32)), "r"(epoch) : "memory");
         }
     }
 }
 
-// Wait for every rank's triple of the current epoch and merge them in rank order.  Called by ONE
-// full warp; every lane returns the same merged moments.
+// Wait for every rank's record of the current epoch and add them up in rank order.  Called by ONE full warp;
+// every lane returns the same moments.  The epoch word and the record are fetched together (the producer kernel
+// of this rank advanced the epoch before this kernel started), so an arrived record costs one round trip.
 __device__ __forceinline__ Moments xch_wait_merge3(const XchRef &x)
 {
     const int lane = threadIdx.x & 31;
     const unsigned char *mine = x.peers[x.rank];
-    const uint32_t epoch = *reinterpret_cast<const volatile uint32_t *>(mine);
-    const int par = (int)(epoch & 1u);
-    double v[3] = {0.0, 0.0, 0.0};
+    double v[4] = {0.0, 0.0, 0.0, 0.0};
+    bool timed_out = false;
     if (lane < x.world) {
-        const uint2 *src = reinterpret_cast<const uint2 *>(mine + xch_ll_offset(x.world)) +
-                           ((size_t)par * x.world + lane) * 6;
         const long long t0 = clock64();
+        while (true) {
+            const uint32_t epoch = *reinterpret_cast<const volatile uint32_t *>(mine);
+            const uint2 *src = reinterpret_cast<const uint2 *>(mine + xch_ll_offset(x.world)) +
+                               ((size_t)(epoch & 1u) * x.world + lane) * 8;
+            uint4 q[4];
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            uint32_t lo, f0, hi, f1;
-            while (true) {
+            for (int i = 0; i < 4; ++i)
                 asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];"
-                             : "=r"(lo), "=r"(f0), "=r"(hi), "=r"(f1) : "l"(src + 2 * i) : "memory");
-                if (f0 == epoch && f1 == epoch) break;
-                if (clock64() - t0 > 20000000000LL) __trap();  // a peer died: do not hang the GPU forever
+                             : "=r"(q[i].x), "=r"(q[i].y), "=r"(q[i].z), "=r"(q[i].w) : "l"(src + 2 * i) : "memory");
+            bool ok = true;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) ok = ok && q[i].y == epoch && q[i].w == epoch;
+            if (ok) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    v[i] = __longlong_as_double((long long)(((unsigned long long)q[i].z << 32) | (unsigned long long)q[i].x));
+                break;
             }
-            v[i] = __longlong_as_double((long long)(((unsigned long long)hi << 32) | (unsigned long long)lo));
+            if (clock64() - t0 > 20000000000LL) { timed_out = true; break; }  // a peer died: give up after ~10 s
         }
     }
-    Moments acc;
-    acc.n = 0.0; acc.mean = 0.0; acc.m2 = 0.0;
+    Sums acc;
+    acc.n = 0.0; acc.s1 = 0.0; acc.s2 = 0.0; acc.piv = 0.0;
     for (int r = 0; r < x.world; ++r) {  // rank order, identical on every rank and lane
-        Moments m;
-        m.n = __shfl_sync(0xffffffffu, v[0], r);
-        m.mean = __shfl_sync(0xffffffffu, v[1], r);
-        m.m2 = __shfl_sync(0xffffffffu, v[2], r);
-        acc = merge(acc, m);
+        Sums q;
+        q.n = __shfl_sync(0xffffffffu, v[0], r);
+        q.s1 = __shfl_sync(0xffffffffu, v[1], r);
+        q.s2 = __shfl_sync(0xffffffffu, v[2], r);
+        q.piv = __shfl_sync(0xffffffffu, v[3], r);
+        if (q.n > 0.0) {
+            if (acc.n == 0.0) acc = q;
+            else {
+                q = rebase(q, acc.piv);
+                acc.n += q.n; acc.s1 += q.s1; acc.s2 += q.s2;
+            }
+        }
     }
-    return acc;
+    Moments m = to_moments(acc);
+    if (__any_sync(0xffffffffu, timed_out)) m.mean = __longlong_as_double(0x7ff8000000000000LL);  // poison, no trap
+    return m;
 }
 
 // ---------------------------------------------------------------------------------
@@ -459,7 +470,7 @@ __device__ __forceinline__ float div_by(float x, float d, float r)
 // ---------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t gx_epoch(const GridXch &g)  // any thread; the epoch of THIS launch
 {
-    return *reinterpret_cast<const volatile uint32_t *>(g.peers[g.rank]) + 1u;
+    return *reinterpret_cast<const volatile uint32_t *>(g.self) + 1u;
 }
 
 __device__ __forceinline__ unsigned char *gx_record(unsigned char *buf, const GridXch &g, uint32_t epoch, int src_rank, int slot)
@@ -470,13 +481,22 @@ __device__ __forceinline__ unsigned char *gx_record(unsigned char *buf, const Gr
 // Publish this CTA's Sums (n, s1, s2, pivot -- read from `mine`, e.g. shared memory, by every participating thread) into
 // slot blockIdx.x of every rank, and empty records into the slots no CTA of this grid owns
 // (blockIdx.x + k * gridDim.x < slots).  Call with all threads of the CTA.
-__device__ __forceinline__ void gx_publish(const GridXch &g, uint32_t epoch, const double *mine)
+// `peer_ptrs`: optional shared-memory copy of g.peers[0 .. world) made early in the kernel (gx_preload_peers),
+// so that no dependent pointer load sits between the end of the scan and the record stores.
+__device__ __forceinline__ void gx_preload_peers(const GridXch &g, unsigned char **peer_ptrs)
 {
+    if ((int)threadIdx.x < g.world) peer_ptrs[threadIdx.x] = g.peers[threadIdx.x];
+}
+
+__device__ __forceinline__ void gx_publish(const GridXch &g, uint32_t epoch, const double *mine,
+                                           unsigned char *const *peer_ptrs = nullptr)
+{
+    if (peer_ptrs == nullptr) peer_ptrs = g.peers;
     const int extra = (g.slots - 1 - (int)blockIdx.x) / (int)gridDim.x + 1;  // slots this CTA fills
     for (int i = threadIdx.x; i < extra * g.world; i += blockDim.x) {
         const int k = i / g.world, r = i - k * g.world;
         const int slot = (int)blockIdx.x + k * (int)gridDim.x;
-        unsigned char *dst = gx_record(g.peers[r], g, epoch, g.rank, slot);
+        unsigned char *dst = gx_record(peer_ptrs[r], g, epoch, g.rank, slot);
 #pragma unroll
         for (int v = 0; v < GX_RECORD_VALS; ++v) {
             const unsigned long long bits = (k == 0) ? (unsigned long long)__double_as_longlong(mine[v]) : 0ull;
@@ -487,7 +507,7 @@ __device__ __forceinline__ void gx_publish(const GridXch &g, uint32_t epoch, con
     }
     __syncthreads();  // the record stores of all threads are issued before the arrival hints
     if ((int)threadIdx.x < g.world) {
-        uint32_t *cnt = reinterpret_cast<uint32_t *>(g.peers[threadIdx.x]) + 4 + (epoch & 1u);
+        uint32_t *cnt = reinterpret_cast<uint32_t *>(peer_ptrs[threadIdx.x]) + 4 + (epoch & 1u);
         asm volatile("red.relaxed.sys.global.add.u32 [%0], %1;" ::"l"(cnt), "r"((uint32_t)extra) : "memory");
     }
 }
@@ -497,7 +517,7 @@ __device__ __forceinline__ void gx_publish(const GridXch &g, uint32_t epoch, con
 // late CTAs' records have to reach).  Returns false on timeout.
 __device__ __forceinline__ bool gx_wait_arrivals(const GridXch &g, uint32_t epoch)
 {
-    const uint32_t *cnt = reinterpret_cast<const uint32_t *>(g.peers[g.rank]) + 4 + (epoch & 1u);
+    const uint32_t *cnt = reinterpret_cast<const uint32_t *>(g.self) + 4 + (epoch & 1u);
     const uint32_t want = (uint32_t)(g.world * g.slots);
     const long long t_start = clock64();
     unsigned ns = 20;
@@ -526,7 +546,7 @@ __device__ __forceinline__ unsigned long long global_timer_ns()
 // divisions of the whole exchange) in thread 0.  `scratch` >= 32 Sums.  All threads of the CTA must call.
 __device__ __forceinline__ Moments gx_collect(const GridXch &g, uint32_t epoch, Sums *scratch)
 {
-    unsigned char *mine = g.peers[g.rank];
+    unsigned char *mine = g.self;
     const int n_rec = g.world * g.slots;
     Sums acc;
     acc.n = 0.0; acc.s1 = 0.0; acc.s2 = 0.0; acc.piv = 0.0;
@@ -601,7 +621,7 @@ __device__ __forceinline__ Moments gx_collect(const GridXch &g, uint32_t epoch, 
 // after that CTA's gx_collect.
 __device__ __forceinline__ void gx_retire(const GridXch &g, uint32_t epoch)
 {
-    uint32_t *hdr = reinterpret_cast<uint32_t *>(g.peers[g.rank]);
+    uint32_t *hdr = reinterpret_cast<uint32_t *>(g.self);
     __threadfence();
     const uint32_t t = atomicAdd(hdr + 1, 1u);
     if (t == gridDim.x - 1) {
@@ -703,14 +723,8 @@ __device__ __forceinline__ void moments_tail(const Sums &mine, const MomentsTail
     if (tail.xch.peers != nullptr) {
         // multi-GPU: hand the rank's moments to every peer; whoever consumes them waits and merges
         if (threadIdx.x < 32) {
-            Moments m;
-            m.n = 0.0; m.mean = 0.0; m.m2 = 0.0;
-            if (threadIdx.x == 0) {
-                m = to_moments(acc);
-                tail.moments_out[0] = m.n; tail.moments_out[1] = m.mean; tail.moments_out[2] = m.m2;
-                *tail.ticket = 0u;
-            }
-            xch_push3(tail.xch, m.n, m.mean, m.m2);
+            if (threadIdx.x == 0) *tail.ticket = 0u;
+            xch_push3(tail.xch, acc);  // lane 0's sums travel; the consumer writes the merged moments_out
         }
         return;
     }

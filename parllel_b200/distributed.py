@@ -85,11 +85,13 @@ class GridExchange:
         self.slots = int(lib.plb_grid_exchange_slots())
         self.ok = self.slots > 0
         self.handle = None
+        self.self_ptr = 0
         single = local or not (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1)
         if single:
             self.group, self.world, self.rank = None, 1, 0
             self.buffer = torch.zeros(lib.plb_grid_exchange_bytes(1, max(self.slots, 1)), dtype=torch.uint8, device=self.device)
             self.peer_table = torch.tensor([self.buffer.data_ptr()], dtype=torch.int64, device=self.device)
+            self.self_ptr = self.buffer.data_ptr()
             return
         self.group = group if group is not None else dist.group.WORLD
         self.world = dist.get_world_size(self.group)
@@ -103,6 +105,7 @@ class GridExchange:
             self.buffer.zero_()
             self.handle = symm_mem.rendezvous(self.buffer, self.group)
             self.peer_table = torch.tensor([int(p) for p in self.handle.buffer_ptrs], dtype=torch.int64, device=self.device)
+            self.self_ptr = int(self.handle.buffer_ptrs[self.rank])
             torch.cuda.synchronize(self.device)
             good = 1
         except Exception as err:  # no peer mapping on this system

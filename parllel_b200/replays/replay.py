@@ -79,7 +79,7 @@ class ReplayBuffer:
         self.batch_transform = batch_transform if batch_transform is not None else (lambda batch: batch)
         self.seed()
 
-        self._paths, self._host, self._ring = [], [], []
+        self._paths, self._host, self._ring, self._host_pinned = [], [], [], []
         self.device = torch.device(device) if device is not None else None
         for path, leaf in _flatten(tree):
             self._paths.append(path)
@@ -92,6 +92,10 @@ class ReplayBuffer:
                 if self.device is None:
                     self.device = default_device()
                 ring = host.to(self.device).contiguous()  # one-time mirror of the whole ring
+                # page-lock the caller's ring in place so the per-iteration refresh is an asynchronous DMA
+                # instead of a blocking pageable copy per leaf (falls back silently if registration is refused)
+                from ..host_pipeline import pin_in_place
+                self._host_pinned.append(bool(host.is_pinned() or pin_in_place(host.numpy())))
             if self.device is None:
                 self.device = ring.device
             assert ring.shape[0] == size_T and ring.shape[1] == sampler_batch_spec.B, \
@@ -101,6 +105,8 @@ class ReplayBuffer:
                 assert size == 1 or stride == want, "feature axes of a replay leaf must be contiguous"
             self._host.append(host)
             self._ring.append(ring)
+            if host is None:
+                self._host_pinned.append(False)
         if len(self._ring) > _lib.GATHER_MAX_LEAVES:
             raise ValueError(f"at most {_lib.GATHER_MAX_LEAVES} leaves per gather launch")
         # host-drawn indices travel through a small ring of pinned staging buffers; each slot carries the
@@ -252,9 +258,11 @@ class ReplayBuffer:
         (device leaves are shared with the writer and need nothing), then advance the write position."""
         T = self.batch_spec.T
         lo = self._cursor
-        for host, ring in zip(self._host, self._ring):
+        for host, ring, pinned in zip(self._host, self._ring, self._host_pinned):
             if host is not None:
-                ring[lo:lo + T].copy_(host[lo:lo + T], non_blocking=False)
+                # the sampler will not touch these rows again before a whole revolution of the ring, so a
+                # stream-ordered DMA out of pinned memory needs no host-side wait
+                ring[lo:lo + T].copy_(host[lo:lo + T], non_blocking=pinned)
         self._cursor = lo + T
         if self._cursor >= self.size_T:  # wrapped: from now on the whole ring holds samples
             self._cursor -= self.size_T * (self._cursor // self.size_T)

@@ -252,6 +252,7 @@ class FusedBatchTransforms(Transform):
             gx = self._grid_exchange(dev)
             if gx.ok:
                 d.gx_peers, d.gx_rank, d.gx_world, d.gx_slots = gx.peer_table.data_ptr(), gx.rank, gx.world, gx.slots
+                d.gx_self = gx.self_ptr
                 keep.append(gx)
         if distributed and phases == _lib.PHASE_ALL and not st.staged and (d.plan & _lib.PLAN_CHUNKED):
             # the round-1 record-per-rank buffers: NormalizeRewards' statistics, and the fallback route
