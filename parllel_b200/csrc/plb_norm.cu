@@ -296,9 +296,12 @@ normalize_advantage_gx_kernel(float *__restrict__ x, int64_t ld_x, int64_t rows,
             v[u] = *reinterpret_cast<const float4 *>(x + off[u]);
         }
     }
-    const uint32_t epoch = gx_epoch(gx);
+    __shared__ uint32_t s_epoch;
+    if (threadIdx.x == 0) s_epoch = gx_epoch(gx);  // one load per CTA (hundreds of CTAs share the word's L2 line)
+    __syncthreads();
+    const uint32_t epoch = s_epoch;
     unsigned char *mine = gx.self;
-    uint4 *result = reinterpret_cast<uint4 *>(mine + 32) + (epoch & 1u);  // {mean bits, epoch, denom bits, epoch}
+    uint4 *result = reinterpret_cast<uint4 *>(mine + GX_RESULT_BYTE) + (epoch & 1u);  // {mean bits, epoch, denom bits, epoch}
     if (blockIdx.x == 0) {
         if (threadIdx.x == 0) gx_wait_arrivals(gx, epoch);
         __syncthreads();

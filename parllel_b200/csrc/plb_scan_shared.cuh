@@ -30,12 +30,16 @@ constexpr size_t XCH_HEADER_BYTES = 1024;  // uint32 epoch @0, uint32 flags[2][w
 // buffer until all world x slots records of the launch epoch have landed and merges them in a fixed
 // order -- so the grid barrier of one GPU and the all-gather across GPUs are the same step, with no
 // atomics, no last-CTA reduction and no second kernel.  Buffer layout (plb_grid_exchange_bytes):
-//     uint32 epoch @0 | uint32 exit_ticket @4 | uint32 status @8 (0 ok, 1 timed out)
-//     uint4 result[2] @32 (by epoch parity): {mean, epoch, denominator, epoch} left by the collector CTA of the
+// (every word that is polled or hit by atomics has a 128-byte line of its own: hundreds of CTAs on one line
+//  serialise in its L2 bank)
+//     line 0:  uint32 epoch @0 | uint32 status @8 (0 ok, 1 timed out)
+//     line 1:  uint32 exit_ticket @128
+//     line 2:  uint32 arrived[2] @256 | line 3:  uint4 result[2] @384     (see below)
+//     uint4 result[2] @384 (by epoch parity): {mean, epoch, denominator, epoch} left by the collector CTA of the
 //            two-kernel route for the other CTAs of its grid (local to the rank)
-//     uint32 arrived[2] @16 (by epoch parity): slots filled so far, a HINT for when to read -- the
+//     uint32 arrived[2] @256 (by epoch parity): slots filled so far, a HINT for when to read -- the
 //            records validate themselves through their epoch tags, so no fence orders it after them
-//     records @256: [2 (epoch parity)][world][slots] x 64 B = 4 x {lo, epoch, hi, epoch} 16-byte units
+//     records @512: [2 (epoch parity)][world][slots] x 64 B = 4 x {lo, epoch, hi, epoch} 16-byte units
 //            carrying the division-free Sums (n, s1, s2, pivot) of one CTA
 struct GridXch {
     unsigned char *const *peers;  // device array [world]: every rank's buffer (world == 1: just ours)
@@ -43,7 +47,8 @@ struct GridXch {
     int rank, world;
     int slots;                    // records per rank and epoch (>= the largest grid of any rank)
 };
-constexpr size_t GX_HEADER_BYTES = 256;
+constexpr size_t GX_HEADER_BYTES = 512;
+constexpr int GX_TICKET_WORD = 32, GX_ARRIVED_WORD = 64, GX_RESULT_BYTE = 384;  // header offsets (words / bytes)
 constexpr size_t GX_RECORD_BYTES = 64;
 constexpr int GX_RECORD_VALS = 4;
 constexpr int GX_MAX_WORLD = 32;
@@ -507,7 +512,7 @@ __device__ __forceinline__ void gx_publish(const GridXch &g, uint32_t epoch, con
     }
     __syncthreads();  // the record stores of all threads are issued before the arrival hints
     if ((int)threadIdx.x < g.world) {
-        uint32_t *cnt = reinterpret_cast<uint32_t *>(peer_ptrs[threadIdx.x]) + 4 + (epoch & 1u);
+        uint32_t *cnt = reinterpret_cast<uint32_t *>(peer_ptrs[threadIdx.x]) + GX_ARRIVED_WORD + (epoch & 1u);
         asm volatile("red.relaxed.sys.global.add.u32 [%0], %1;" ::"l"(cnt), "r"((uint32_t)extra) : "memory");
     }
 }
@@ -517,7 +522,7 @@ __device__ __forceinline__ void gx_publish(const GridXch &g, uint32_t epoch, con
 // late CTAs' records have to reach).  Returns false on timeout.
 __device__ __forceinline__ bool gx_wait_arrivals(const GridXch &g, uint32_t epoch)
 {
-    const uint32_t *cnt = reinterpret_cast<const uint32_t *>(g.self) + 4 + (epoch & 1u);
+    const uint32_t *cnt = reinterpret_cast<const uint32_t *>(g.self) + GX_ARRIVED_WORD + (epoch & 1u);
     const uint32_t want = (uint32_t)(g.world * g.slots);
     const long long t_start = clock64();
     unsigned ns = 20;
@@ -623,12 +628,12 @@ __device__ __forceinline__ void gx_retire(const GridXch &g, uint32_t epoch)
 {
     uint32_t *hdr = reinterpret_cast<uint32_t *>(g.self);
     __threadfence();
-    const uint32_t t = atomicAdd(hdr + 1, 1u);
+    const uint32_t t = atomicAdd(hdr + GX_TICKET_WORD, 1u);
     if (t == gridDim.x - 1) {
-        hdr[1] = 0u;
+        hdr[GX_TICKET_WORD] = 0u;
         // every rank's hints of this epoch have arrived (all CTAs here waited for them), and nobody can send
         // hints of epoch + 2 before this rank has published epoch + 1, i.e. after this launch: safe to clear
-        hdr[4 + (epoch & 1u)] = 0u;
+        hdr[GX_ARRIVED_WORD + (epoch & 1u)] = 0u;
         __threadfence();
         *reinterpret_cast<volatile uint32_t *>(hdr) = epoch;
     }

@@ -94,8 +94,11 @@ class ReplayBuffer:
                 ring = host.to(self.device).contiguous()  # one-time mirror of the whole ring
                 # page-lock the caller's ring in place so the per-iteration refresh is an asynchronous DMA
                 # instead of a blocking pageable copy per leaf (falls back silently if registration is refused)
-                from ..host_pipeline import pin_in_place
-                self._host_pinned.append(bool(host.is_pinned() or pin_in_place(host.numpy())))
+                pinned = False
+                if ring.is_cuda:
+                    from ..host_pipeline import pin_in_place
+                    pinned = bool(host.is_pinned() or pin_in_place(host.numpy()))
+                self._host_pinned.append(pinned)
             if self.device is None:
                 self.device = ring.device
             assert ring.shape[0] == size_T and ring.shape[1] == sampler_batch_spec.B, \
