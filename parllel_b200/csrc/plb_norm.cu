@@ -274,7 +274,10 @@ normalize_advantage_xch_kernel(float *__restrict__ x, int64_t ld_x, int64_t rows
 // leaves (mean, denominator) as one epoch-tagged 16-byte unit in the local buffer header; every other CTA spins
 // on that single unit (one small load per poll) with its first loads already in flight.  No serial tail in the
 // producer, no NCCL, no host round trip; the last CTA out retires the epoch.
-__global__ void __launch_bounds__(256)
+// (minBlocksPerMultiprocessor = 4 caps the registers at 64: the collector path of CTA 0 spills a little, but the
+//  streaming CTAs keep the occupancy of the plain normalise kernel -- at 158 registers they ran one CTA per SM and
+//  the kernel took 18 us instead of 9)
+__global__ void __launch_bounds__(256, 4)
 normalize_advantage_gx_kernel(float *__restrict__ x, int64_t ld_x, int64_t rows, int64_t cols, const GridXch gx,
                               float eps, double *__restrict__ moments_out)
 {
