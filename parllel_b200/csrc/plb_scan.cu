@@ -778,6 +778,7 @@ static int g_resident_poll = 0;          // experiments: 1 = every thread polls 
 static int g_sharded_route = 0;          // sharded step: 0 auto, 1 resident kernel, 2 two kernels + grid exchange, 3 legacy (key 17)
 int sharded_route() { return g_sharded_route; }
 static unsigned long long *g_debug_buf = nullptr;  // plb_debug_set_buffer
+unsigned long long *debug_buffer() { return g_debug_buf; }
 
 template <int MODE, typename ACC, int NW, int R, bool HAS_PRE, bool HAS_STATS>
 static int launch_chunked_inst(const chunked::TensorMaps &tm, chunked::Params p, int sms, cudaStream_t stream)

@@ -114,6 +114,7 @@ bool scan_chunked_supported(const float *reward, int64_t ld_r, const float *valu
                             const uint8_t *done, int64_t ld_d, int64_t T, int64_t B, int64_t inner);
 bool resident_wanted(int world);  // policy (plb_set_tuning key 12)
 int sharded_route();              // plb_set_tuning key 17
+unsigned long long *debug_buffer();  // plb_debug_set_buffer
 bool resident_supported(const float *reward, int64_t ld_r, const float *value, int64_t ld_v, const uint8_t *done,
                         int64_t ld_d, const float *adv, int64_t ld_a, const float *ret, int64_t ld_t,
                         int64_t T, int64_t B);
