@@ -28,6 +28,7 @@ NVCC_FLAGS = [
     # runtime would bake every cudart entry-point name into the artefact
     "-shared", "-cudart", "shared",
     "-Xlinker", "-rpath,/usr/local/cuda/lib64",
+    "-Xlinker", "--no-undefined",   # a definition lost in an edit must fail the build, not the first dlopen
 ]
 
 
