@@ -75,12 +75,13 @@ static int run_pipeline(const plb_batch_pipeline *d, int phases, cudaStream_t st
     gx.rank = d->gx_rank; gx.world = d->gx_world; gx.slots = d->gx_slots;
     PLB_REQUIRE(gx.peers == nullptr || gx.self != nullptr, PLB_ERR_INVALID_ARGUMENT, "gx_peers without gx_self");
     // sharded batches (gx.world > 1) have three routes for EstimateAdvantage + NormalizeAdvantage (key 17):
-    //   2 (auto)  two kernels + grid exchange: the scan's CTAs publish their partial sums to every rank as they
-    //             retire, the normalise kernel's collector CTA adds them up while the other CTAs' loads are in flight;
+    //   3 (auto)  last-CTA reduction in the scan, ONE record of partial sums per rank pushed to every rank, every CTA
+    //             of the normalise kernel adds the `world` records up itself (xch_push3 / xch_wait_merge3);
     //   1         the resident kernel (one launch; its write-only final phase runs at ~half of HBM speed);
-    //   3         legacy: last-CTA reduction in the scan, one record per rank (xch_push3 / xch_wait_merge3)
+    //   2         two kernels + grid exchange: the scan's CTAs publish their partial sums to every rank as they
+    //             retire, a collector CTA of the normalise kernel adds them up and hands the result to the others
     const bool multi = gx.peers != nullptr && gx.world > 1;
-    const int route = sharded_route() == 0 ? 2 : sharded_route();
+    const int route = sharded_route() == 0 ? 3 : sharded_route();
     const bool both_phases = est_adv && norm_adv && (phases & PLB_PHASE_B) && (phases & PLB_PHASE_C) && !split_partials;
     const bool want_resident = both_phases && gx.peers != nullptr && (plan & PLB_PLAN_RESIDENT) &&
                                (multi ? (route == 1 && plan != PLB_PLAN_AUTO) : resident_wanted(1));

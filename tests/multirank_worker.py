@@ -96,8 +96,8 @@ def main():
 
     # ---- 1. C4-shaped step (EstimateAdvantage + NormalizeAdvantage): every exchange route, lambda 0.95 and 1.0 ----
     T, B = 256, 65536
-    routes = {2: "two kernels + grid exchange (default)", 1: "resident kernel", 3: "last-CTA reduction + record per rank"}
-    for lam, route in ((0.95, 2), (0.95, 1), (0.95, 3), (1.0, 2), (1.0, 1)):
+    routes = {3: "last-CTA reduction + record per rank (default)", 1: "resident kernel", 2: "two kernels + grid exchange"}
+    for lam, route in ((0.95, 3), (0.95, 1), (0.95, 2), (1.0, 3), (1.0, 1)):
         _lib.load().plb_set_tuning(17, route)
         g = synth(2, T, B)
         adv, ret = np.empty_like(g["value"]), np.empty_like(g["value"])

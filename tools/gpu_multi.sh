@@ -1,20 +1,21 @@
 #!/bin/bash
-# usage: bash tools/gpu_multi.sh N   -- multi-rank parity test + bench on N GPUs of one box
+# usage: bash tools/gpu_multi.sh N ["worlds"]   -- multi-rank parity test + bench on N GPUs of one box
 N=$1
+WORLDS=${2:-"2 4 8"}
 mkdir -p gpurun_out
 nvidia-smi -L > gpurun_out/multi${N}_smi.log 2>&1
 timeout 900 python -m pytest tests/test_gpu_multirank.py -q -m gpu -x > gpurun_out/multi${N}_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/multi${N}_pytest.log
 tail -25 gpurun_out/multi${N}_pytest.log
-for W in 2 4 8; do
+for W in $WORLDS; do
   if [ $W -le $N ]; then
     timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $W --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $W --steps 1000 --warmup 10 > gpurun_out/bench_n${W}.json 2> gpurun_out/bench_n${W}.err; echo "bench N=$W rc=$?"
     tail -c 1500 gpurun_out/bench_n${W}.json; tail -5 gpurun_out/bench_n${W}.err
-    for R in 1 3; do
+    for R in 1 2; do
       PLB_TUNING=17=$R timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $W --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $W --steps 500 --warmup 10 --windows 3 > gpurun_out/bench_n${W}_route$R.json 2> gpurun_out/bench_n${W}_route$R.err; echo "bench N=$W route $R rc=$?"
     done
     python - <<PY
 import json
-for tag in ("", "_route1", "_route3"):
+for tag in ("", "_route1", "_route2"):
     try:
         for line in open("gpurun_out/bench_n${W}%s.json" % tag):
             if line.startswith("{"):
