@@ -25,6 +25,7 @@ import torch
 from .. import _lib
 from .._leaves import Staging, previous_row, rows_2d, stream_ptr
 from ..arrays import DeviceArray
+from ..tree import ArrayDict
 from .advantage import EstimateAdvantage
 from .clip_rewards import ClipRewards
 from .norm_advantage import EPSILON as ADV_EPSILON
@@ -64,7 +65,7 @@ class FusedBatchTransforms(Transform):
         self._moments = None
         self._graphs: dict = {}
         self._seen: set = set()
-        # replay fast path: (signature of the leaves the tree holds NOW, phases) -> captured graph
+        # replay fast path: (id(tree), phases) -> (identity + address checks of its leaves, captured graph)
         self._bound: dict = {}
         self._gx = None          # grid-exchange buffers of the resident advantage kernel
         self._plans: dict = {}   # descriptor bytes -> plan bits agreed across the ranks
@@ -90,26 +91,6 @@ class FusedBatchTransforms(Transform):
             base = leaf.base
             return (base.data_ptr(), leaf._start, leaf._T, base.shape, leaf.padding)
         return None
-
-    def _signature(self, sample_tree):
-        """Signature of the leaves `sample_tree` holds at this call, or None if any is not on the device.
-        Looked up afresh every call: a leaf replaced inside the same dict, or a new dict that happens to
-        reuse a dead one's id, must never replay a graph bound to other tensors."""
-        sig = []
-        for name in self._LEAF_NAMES:
-            if name in sample_tree:
-                one = self._leaf_signature(sample_tree[name])
-                if one is None:
-                    return None
-                sig.append(one)
-            else:
-                sig.append(None)
-        if "agent_info" in sample_tree and "value" in sample_tree["agent_info"]:
-            one = self._leaf_signature(sample_tree["agent_info"]["value"])
-            if one is None:
-                return None
-            sig.append(one)
-        return tuple(sig)
 
     def _grid_exchange(self, dev):
         """Buffers through which every CTA of every rank trades its partial advantage moments inside the
@@ -140,17 +121,39 @@ class FusedBatchTransforms(Transform):
             self._plans[key] = plan
         return plan
 
+    @staticmethod
+    def _address(leaf) -> int:
+        """Where a device leaf's visible window starts right now (rotation of a DeviceArray included)."""
+        if type(leaf) is torch.Tensor:
+            return leaf.data_ptr()
+        if isinstance(leaf, DeviceArray):
+            return leaf.base.data_ptr() + leaf._start * leaf.base.stride(0) * leaf.base.element_size()
+        return leaf.data_ptr()
+
+    def _still_bound(self, sample_tree, checks) -> bool:
+        """The replay fast path's guard: every leaf the graph was captured for is still THE object the tree
+        holds under that name (identity: a replaced leaf, or a new dict that reuses a dead dict's id, cannot
+        pass, because the binding keeps the captured leaves alive) and still exposes the same memory."""
+        get = sample_tree._dict.get if type(sample_tree) is ArrayDict else sample_tree.get
+        for name, sub, leaf, address in checks:
+            cur = get(name)
+            if sub is not None and cur is not None:
+                cur = cur._dict.get(sub) if type(cur) is ArrayDict else cur.get(sub)
+            if cur is not leaf or self._address(leaf) != address:
+                return False
+        return True
+
     def __call__(self, sample_tree, phases: int = _lib.PHASE_ALL):
-        # fast path: a graph was captured for exactly these leaves (same memory, same geometry) -> replay it;
+        # fast path: a graph was captured for exactly these leaves -> replay it (a few microseconds of host time,
+        # which matters: the sharded step re-synchronises all ranks every ~30 us, so the slowest host paces them);
         # inside somebody else's stream capture the launches are enqueued as they are (no nested graphs)
-        capturing = torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()
-        sig = None
-        if self.use_cuda_graph and not capturing and self._bound:
-            sig = self._signature(sample_tree)
-            graph = self._bound.get((sig, phases)) if sig is not None else None
-            if graph is not None:
-                graph.replay()
+        if self._bound:
+            entry = self._bound.get((id(sample_tree), phases))
+            if entry is not None and self._still_bound(sample_tree, entry[0]) \
+                    and not torch.cuda.is_current_stream_capturing():
+                entry[1].replay()
                 return sample_tree
+        capturing = torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()
         nr, est, na = self.norm_rewards, self.estimate, self.norm_adv
         lib = _lib.load()
         st = Staging(nr.return_statistics.device if nr is not None else None)
@@ -290,7 +293,7 @@ class FusedBatchTransforms(Transform):
             graph = self._graphs.get(key)
             if graph is not None:
                 graph[0].replay()
-                self._bind(sample_tree, phases, graph[0], sig)
+                self._bind(sample_tree, phases, graph[0])
             elif key not in self._seen:
                 self._seen.add(key)  # first sight: run eagerly (also configures the kernels)
                 enqueue()
@@ -305,12 +308,20 @@ class FusedBatchTransforms(Transform):
         st.finish()
         return sample_tree
 
-    def _bind(self, sample_tree, phases: int, graph, sig=None) -> None:
-        """Remember the graph under the signature of the device leaves it was captured for."""
-        if sig is None:
-            sig = self._signature(sample_tree)
-        if sig is None:
-            return
+    def _bind(self, sample_tree, phases: int, graph) -> None:
+        """Remember the graph for this tree object together with the device leaves it was captured for."""
+        checks = []
+        for name in self._LEAF_NAMES:
+            if name in sample_tree:
+                leaf = sample_tree[name]
+                if self._leaf_signature(leaf) is None:
+                    return  # host leaf: never replayed
+                checks.append((name, None, leaf, self._address(leaf)))
+        if "agent_info" in sample_tree and "value" in sample_tree["agent_info"]:
+            leaf = sample_tree["agent_info"]["value"]
+            if self._leaf_signature(leaf) is None:
+                return
+            checks.append(("agent_info", "value", leaf, self._address(leaf)))
         if len(self._bound) > 256:
             self._bound.clear()
-        self._bound[(sig, phases)] = graph
+        self._bound[(id(sample_tree), phases)] = (checks, graph)
