@@ -344,6 +344,7 @@ __device__ __forceinline__ Moments xch_wait_merge3(const XchRef &x)
     bool timed_out = false;
     if (lane < x.world) {
         const long long t0 = clock64();
+        unsigned ns = 32;
         while (true) {
             const uint32_t epoch = *reinterpret_cast<const volatile uint32_t *>(mine);
             const uint2 *src = reinterpret_cast<const uint2 *>(mine + xch_ll_offset(x.world)) +
@@ -363,6 +364,10 @@ __device__ __forceinline__ Moments xch_wait_merge3(const XchRef &x)
                 break;
             }
             if (clock64() - t0 > 20000000000LL) { timed_out = true; break; }  // a peer died: give up after ~10 s
+            // back off: hundreds of CTAs spinning on the same few lines would slow down the very NVLink stores
+            // (and the epoch update) they are waiting for
+            __nanosleep(ns);
+            if (ns < 256) ns <<= 1;
         }
     }
     Sums acc;
