@@ -210,14 +210,16 @@ normalize_advantage_partials_kernel(float *__restrict__ x, int64_t ld_x, int64_t
 // for all ranks' flags and merges in rank order in its prologue (warp 0), the first loads in flight.
 __global__ void __launch_bounds__(256)
 normalize_advantage_xch_kernel(float *__restrict__ x, int64_t ld_x, int64_t rows, int64_t cols, const XchRef xch,
-                               float eps, double *__restrict__ moments_out)
+                               float eps, double *__restrict__ moments_out, unsigned long long *dbg)
 {
     __shared__ float s_mean, s_denom;
+    if (dbg != nullptr && threadIdx.x == 0 && blockIdx.x == 0) dbg[4] = global_timer_ns();
     // the wait comes first, on an idle memory pipe (see normalize_advantage_gx_kernel): polls queued behind the
     // grid's first wave of streaming loads take microseconds each
     if (threadIdx.x < 32) {
         const Moments m = xch_wait_merge3(xch);
         if (threadIdx.x == 0) {
+            if (dbg != nullptr && blockIdx.x == 0) dbg[5] = global_timer_ns();
             s_mean = __double2float_rn(m.mean);
             s_denom = __fadd_rn(__double2float_rn(sqrt(m.m2 / m.n)), eps);
             if (blockIdx.x == 0) {
@@ -257,6 +259,7 @@ normalize_advantage_xch_kernel(float *__restrict__ x, int64_t ld_x, int64_t rows
             }
         }
     }
+    if (dbg != nullptr && threadIdx.x == 0 && blockIdx.x == 0) dbg[6] = global_timer_ns();
 }
 
 // Consumer of the grid exchange on the two-kernel route: the advantage scan of every rank published one record
@@ -398,7 +401,8 @@ int normalize_advantage_after_exchange(float *x, int64_t ld_x, int64_t rows, int
     int64_t blocks = ceil_div(rows * cols / 4, 256 * 4);
     if (blocks < 1) blocks = 1;
     if (blocks > (int64_t)sms * g_normadv_ctas_per_sm) blocks = (int64_t)sms * g_normadv_ctas_per_sm;
-    normalize_advantage_xch_kernel<<<(unsigned)blocks, 256, 0, stream>>>(x, ld_x, rows, cols, xch, (float)eps, moments_out);
+    normalize_advantage_xch_kernel<<<(unsigned)blocks, 256, 0, stream>>>(x, ld_x, rows, cols, xch, (float)eps, moments_out,
+                                                                         debug_buffer());
     PLB_LAUNCH_CHECK();
     return PLB_OK;
 }

@@ -166,6 +166,7 @@ static int run_pipeline(const plb_batch_pipeline *d, int phases, cudaStream_t st
                 f.tail = make_tail(d->advantage_moments, ws_b);
                 f.tail.partials_only = direct_partials ? 1 : 0;
                 if (use_xch) f.tail.xch = xch;
+                f.tail.dbg = debug_buffer();
             }
             const int mode = (d->gae_lambda == 1.0) ? 1 : 0;
             const bool resident = want_resident &&

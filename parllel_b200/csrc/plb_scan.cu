@@ -291,6 +291,7 @@ scan_pipelined_kernel(const __grid_constant__ TensorMaps tm, const Params p)
     __shared__ unsigned char *s_peers[GX_MAX_WORLD];
     if (RESIDENT) gx_preload_peers(p.gx, s_peers);
     if (RESIDENT && p.dbg != nullptr && threadIdx.x == 0) p.dbg[blockIdx.x * 8 + 0] = global_timer_ns();
+    if (!RESIDENT && HAS_STATS && p.tail.dbg != nullptr && threadIdx.x == 0 && blockIdx.x == 0) p.tail.dbg[0] = global_timer_ns();
     if (threadIdx.x == 0) {
         for (int s = 0; s < n_stages; ++s) mbar_init(&sh->full[s], 1);
         fence_proxy_async_smem();

@@ -74,6 +74,7 @@ struct MomentsTail {
     // optional: instead of any local reduction, every CTA publishes its partial sums into the grid-exchange
     // records of every rank (gx_publish); the consumer kernel collects them (normalize_advantage_after_gx)
     GridXch gx;
+    unsigned long long *dbg;  // experiments: %globaltimer stamps of the sharded step (plb_debug_set_buffer), or NULL
 };
 
 static inline MomentsTail make_tail(double *moments_out, void *workspace)
@@ -87,6 +88,7 @@ static inline MomentsTail make_tail(double *moments_out, void *workspace)
     t.upd_flags = 0;
     t.xch.peers = nullptr; t.xch.rank = 0; t.xch.world = 1;
     t.gx.peers = nullptr; t.gx.self = nullptr; t.gx.rank = 0; t.gx.world = 1; t.gx.slots = 0;
+    t.dbg = nullptr;
     return t;
 }
 
@@ -711,6 +713,7 @@ __device__ __forceinline__ void moments_tail(const Sums &mine, const MomentsTail
     __syncthreads();
     if (!is_last) return;
     __threadfence();
+    if (tail.dbg != nullptr && threadIdx.x == 0) tail.dbg[1] = global_timer_ns();
     // contiguous slices per thread keep the summation order = CTA index order
     const unsigned n = gridDim.x;
     const unsigned per = (n + blockDim.x - 1) / blockDim.x;
@@ -735,7 +738,9 @@ __device__ __forceinline__ void moments_tail(const Sums &mine, const MomentsTail
         // multi-GPU: hand the rank's moments to every peer; whoever consumes them waits and merges
         if (threadIdx.x < 32) {
             if (threadIdx.x == 0) *tail.ticket = 0u;
+            if (tail.dbg != nullptr && threadIdx.x == 0) tail.dbg[2] = global_timer_ns();
             xch_push3(tail.xch, acc);  // lane 0's sums travel; the consumer writes the merged moments_out
+            if (tail.dbg != nullptr && threadIdx.x == 0) tail.dbg[3] = global_timer_ns();
         }
         return;
     }
