@@ -210,21 +210,54 @@ normalize_advantage_partials_kernel(float *__restrict__ x, int64_t ld_x, int64_t
 // for all ranks' flags and merges in rank order in its prologue (warp 0), the first loads in flight.
 __global__ void __launch_bounds__(256)
 normalize_advantage_xch_kernel(float *__restrict__ x, int64_t ld_x, int64_t rows, int64_t cols, const XchRef xch,
-                               float eps, double *__restrict__ moments_out, unsigned long long *dbg)
+                               float eps, double *__restrict__ moments_out, unsigned long long *dbg, int collector)
 {
     __shared__ float s_mean, s_denom;
     if (dbg != nullptr && threadIdx.x == 0 && blockIdx.x == 0) dbg[4] = global_timer_ns();
     // the wait comes first, on an idle memory pipe (see normalize_advantage_gx_kernel): polls queued behind the
-    // grid's first wave of streaming loads take microseconds each
-    if (threadIdx.x < 32) {
-        const Moments m = xch_wait_merge3(xch);
-        if (threadIdx.x == 0) {
-            if (dbg != nullptr && blockIdx.x == 0) dbg[5] = global_timer_ns();
-            s_mean = __double2float_rn(m.mean);
-            s_denom = __fadd_rn(__double2float_rn(sqrt(m.m2 / m.n)), eps);
-            if (blockIdx.x == 0) {
-                moments_out[0] = m.n; moments_out[1] = m.mean; moments_out[2] = m.m2;
+    // grid's first wave of streaming loads take microseconds each.
+    // collector != 0: only CTA 0 polls the ranks' records; it leaves (mean, denominator) as ONE epoch-tagged unit in
+    // the local buffer and every other CTA polls that unit with back-off -- with hundreds of CTAs x `world` lanes on
+    // the record lines, even records that had long arrived took 3.2 us to read at 8 ranks (1.3 us at 2)
+    const unsigned char *mine = xch.peers[xch.rank];
+    uint4 *result = reinterpret_cast<uint4 *>(const_cast<unsigned char *>(mine) + XCH_RESULT_BYTE);
+    if (collector == 0 || blockIdx.x == 0) {
+        if (threadIdx.x < 32) {
+            const Moments m = xch_wait_merge3(xch);
+            if (threadIdx.x == 0) {
+                if (dbg != nullptr && blockIdx.x == 0) dbg[5] = global_timer_ns();
+                const float mean = __double2float_rn(m.mean);
+                const float denom = __fadd_rn(__double2float_rn(sqrt(m.m2 / m.n)), eps);
+                s_mean = mean; s_denom = denom;
+                if (blockIdx.x == 0) {
+                    if (collector != 0) {
+                        const uint32_t epoch = *reinterpret_cast<const volatile uint32_t *>(mine);
+                        asm volatile("st.relaxed.sys.global.v4.u32 [%0], {%1, %2, %3, %4};"
+                                     ::"l"(result + (epoch & 1u)), "r"(__float_as_uint(mean)), "r"(epoch),
+                                       "r"(__float_as_uint(denom)), "r"(epoch) : "memory");
+                    }
+                    moments_out[0] = m.n; moments_out[1] = m.mean; moments_out[2] = m.m2;
+                }
             }
+        }
+    } else if (threadIdx.x == 0) {
+        const long long t0 = clock64();
+        unsigned ns = 32;
+        while (true) {
+            const uint32_t epoch = *reinterpret_cast<const volatile uint32_t *>(mine);
+            uint4 q;
+            asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "l"(result + (epoch & 1u)) : "memory");
+            if (q.y == epoch && q.w == epoch && epoch != 0u) {
+                s_mean = __uint_as_float(q.x); s_denom = __uint_as_float(q.z);
+                break;
+            }
+            if (clock64() - t0 > 20000000000LL) {  // the collector never finished: poison instead of hanging
+                s_mean = __uint_as_float(0x7fc00000u); s_denom = 1.f;
+                break;
+            }
+            __nanosleep(ns);
+            if (ns < 256) ns <<= 1;
         }
     }
     __syncthreads();
@@ -402,7 +435,7 @@ int normalize_advantage_after_exchange(float *x, int64_t ld_x, int64_t rows, int
     if (blocks < 1) blocks = 1;
     if (blocks > (int64_t)sms * g_normadv_ctas_per_sm) blocks = (int64_t)sms * g_normadv_ctas_per_sm;
     normalize_advantage_xch_kernel<<<(unsigned)blocks, 256, 0, stream>>>(x, ld_x, rows, cols, xch, (float)eps, moments_out,
-                                                                         debug_buffer());
+                                                                         debug_buffer(), xch_collector());
     PLB_LAUNCH_CHECK();
     return PLB_OK;
 }

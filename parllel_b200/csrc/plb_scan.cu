@@ -787,6 +787,8 @@ static int g_resident_plain_launch = 0;  // experiments: 1 = no cooperative-laun
 static int g_resident_poll = 0;          // experiments: 1 = every thread polls its own records (key 15)
 static int g_sharded_route = 0;          // sharded step: 0 auto, 1 resident kernel, 2 two kernels + grid exchange, 3 legacy (key 17)
 int sharded_route() { return g_sharded_route; }
+static int g_xch_collector = 1;          // record-per-rank consumer: 1 = one collector CTA + tagged result, 0 = every CTA polls (key 18)
+int xch_collector() { return g_xch_collector; }
 static unsigned long long *g_debug_buf = nullptr;  // plb_debug_set_buffer
 unsigned long long *debug_buffer() { return g_debug_buf; }
 
@@ -1188,6 +1190,7 @@ int plb_set_tuning(int key, int value)
         case 13: plb::set_rng_cluster(value); return PLB_OK;
         case 16: plb::set_gather_mode(value); return PLB_OK;
         case 17: plb::g_sharded_route = value; return PLB_OK;
+        case 18: plb::g_xch_collector = value; return PLB_OK;
         case 14: plb::g_resident_plain_launch = value; return PLB_OK;
         case 15: plb::g_resident_poll = value; return PLB_OK;
         case 5: plb::g_scan_debug = value; return PLB_OK;

@@ -22,7 +22,8 @@ struct XchRef {
     unsigned char *const *peers;  // device array [world] of every rank's buffer, peer-mapped
     int rank, world;
 };
-constexpr size_t XCH_HEADER_BYTES = 1024;  // uint32 epoch @0, uint32 flags[2][world] @64, data @1024
+constexpr size_t XCH_HEADER_BYTES = 1024;  // uint32 epoch @0, uint32 flags[2][world] @64, uint4 result[2] @768, data @1024
+constexpr size_t XCH_RESULT_BYTE = 768;    // {mean, epoch, denominator, epoch} by epoch parity: collector CTA -> the others
 
 // Grid-wide + cross-GPU statistics exchange of the resident advantage kernel (one protocol for both):
 // every CTA of every rank stores its partial (count, mean, M2) as an epoch-tagged record straight into
@@ -116,6 +117,7 @@ bool scan_chunked_supported(const float *reward, int64_t ld_r, const float *valu
                             const uint8_t *done, int64_t ld_d, int64_t T, int64_t B, int64_t inner);
 bool resident_wanted(int world);  // policy (plb_set_tuning key 12)
 int sharded_route();              // plb_set_tuning key 17
+int xch_collector();              // plb_set_tuning key 18
 unsigned long long *debug_buffer();  // plb_debug_set_buffer
 bool resident_supported(const float *reward, int64_t ld_r, const float *value, int64_t ld_v, const uint8_t *done,
                         int64_t ld_d, const float *adv, int64_t ld_a, const float *ret, int64_t ld_t,

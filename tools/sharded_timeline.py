@@ -17,33 +17,30 @@ T, B = 1024, 4096
 trees = [ArrayDict({"reward": torch.randn(T, B, device=dev), "done": torch.rand(T, B, device=dev) < 0.01,
                     "agent_info": {"value": torch.randn(T, B, device=dev)}, "bootstrap_value": torch.randn(B, device=dev),
                     "advantage": torch.empty(T, B, device=dev), "return_": torch.empty(T, B, device=dev)}) for _ in range(6)]
+for item in filter(None, os.environ.get("PLB_TUNING", "").split(",")):
+    pass  # applied by _lib.load()
+buf = torch.zeros(64, dtype=torch.int64, device=dev)
+lib.plb_debug_set_buffer(buf.data_ptr())  # set BEFORE capture: the pointer is a launch argument baked into the graphs
 fz = FusedBatchTransforms([EstimateAdvantage(0.99, 0.95), NormalizeAdvantage(trees[0])])
 for i in range(30):
     fz(trees[i % 6])
 torch.cuda.synchronize(); dist.barrier()
-buf = torch.zeros(64, dtype=torch.int64, device=dev)
 rows = []
-for rep in range(40):  # the debug pointer is a launch argument: eager launches only (graphs captured it as NULL)
-    pass
-fz2 = FusedBatchTransforms([EstimateAdvantage(0.99, 0.95), NormalizeAdvantage(trees[0])], use_cuda_graph=False)
-lib.plb_debug_set_buffer(buf.data_ptr())
-for i in range(60):
-    fz2(trees[i % 6])
-    if i >= 20:
-        torch.cuda.synchronize()
-        t = buf.cpu().numpy().astype(np.float64)
-        rows.append([(t[k] - t[0]) / 1e3 for k in range(7)])
-        # keep the ranks loosely in step like a back-to-back run would
-lib.plb_debug_set_buffer(0)
+for rep in range(20):  # 20 bursts of 100 back-to-back graph replays; the stamps of each burst's LAST step are read
+    for i in range(100):
+        fz(trees[i % 6])
+    torch.cuda.synchronize()
+    t = buf.cpu().numpy().astype(np.float64)
+    rows.append([(t[k] - t[0]) / 1e3 for k in range(7)])
+    dist.barrier()
 r = np.median(np.array(rows), axis=0)
 names = ["scan start", "last CTA reached", "reduced", "pushed", "normalise start", "records seen", "normalise end"]
 line = f"rank {rank}: " + "  ".join(f"{n} {v:6.2f}" for n, v in zip(names, r)) + f"   | wait {r[5] - r[4]:5.2f} us, launch gap {r[4] - r[3]:5.2f} us"
 gathered = [None] * world
 dist.all_gather_object(gathered, line)
 if rank == 0:
-    print(f"world {world}, eager launches (host-paced), medians of 40 steps, us relative to the scan's start:")
+    print(f"world {world}, PLB_TUNING={os.environ.get('PLB_TUNING', '')}: back-to-back graph replays, last step of 20 bursts (medians), us relative to the scan's start:")
     print("\n".join(gathered))
-# now back-to-back graph replays with timing, for reference
 torch.cuda.synchronize(); dist.barrier()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
@@ -52,5 +49,6 @@ for i in range(600):
 e1.record(); torch.cuda.synchronize()
 if rank == 0:
     print(f"graph replay: {e0.elapsed_time(e1) / 600 * 1e3:.2f} us per step")
+lib.plb_debug_set_buffer(0)
 dist.barrier()
 os._exit(0)
