@@ -67,6 +67,10 @@ PLB_API const char *plb_last_error(void);
 /* Kernels this process has ENQUEUED through the library so far (launches recorded into a CUDA graph
  * under capture count once, at capture): out2[0] = all kernels, out2[1] = resident advantage kernels. */
 PLB_API void plb_launch_counters(int64_t *out2);
+/* cudaGraphLaunch of an instantiated graph (a cudaGraphExec_t, e.g. torch.cuda.CUDAGraph.raw_cuda_graph_exec()) on
+ * `stream`: the replay fast path of the Python classes, a few microseconds cheaper per call than going through the
+ * framework's replay wrapper -- with B sharded over 8 GPUs the slowest host paces every rank. */
+PLB_API int plb_graph_launch(void *graph_exec, plb_stream_t stream);
 /* Number of SMs of the current device (grid sizing); <0 on error. */
 PLB_API int plb_sm_count(void);
 /* Tuning / diagnostics knobs (process-wide; used by tools/ and the tests, not by the transforms).

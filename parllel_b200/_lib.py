@@ -65,6 +65,7 @@ _SIGNATURES = {
     "plb_version": ([], c_int),
     "plb_last_error": ([], ctypes.c_char_p),
     "plb_sm_count": ([], c_int),
+    "plb_graph_launch": ([c_void_p, c_void_p], c_int),
     "plb_launch_counters": ([ctypes.POINTER(c_int64)], None),
     "plb_set_tuning": ([c_int, c_int], c_int),
     "plb_debug_set_buffer": ([c_void_p], None),

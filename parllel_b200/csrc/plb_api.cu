@@ -52,6 +52,14 @@ void plb_launch_counters(int64_t *out2)
     out2[1] = __atomic_load_n(&plb::g_resident_launches, __ATOMIC_RELAXED);
 }
 
+int plb_graph_launch(void *graph_exec, plb_stream_t stream)
+{
+    using namespace plb;
+    PLB_REQUIRE(graph_exec != nullptr, PLB_ERR_INVALID_ARGUMENT, "null graph");
+    PLB_CUDA(cudaGraphLaunch(reinterpret_cast<cudaGraphExec_t>(graph_exec), (cudaStream_t)stream));
+    return PLB_OK;
+}
+
 int plb_sm_count(void)
 {
     const int n = plb::sm_count();

@@ -150,8 +150,14 @@ class FusedBatchTransforms(Transform):
         if self._bound:
             entry = self._bound.get((id(sample_tree), phases))
             if entry is not None and self._still_bound(sample_tree, entry[0]) \
-                    and not torch.cuda.is_current_stream_capturing():
-                entry[1].replay()
+                    and not torch._C._cuda_isCurrentStreamCapturing():
+                launch, exec_ptr, dev_index = entry[2]
+                if launch is not None:  # cudaGraphLaunch through the C ABI on the caller's current stream
+                    rc = launch(exec_ptr, torch._C._cuda_getCurrentRawStream(dev_index))
+                    if rc:
+                        _lib.check(rc, "plb_graph_launch")
+                else:
+                    entry[1].replay()
                 return sample_tree
         capturing = torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()
         nr, est, na = self.norm_rewards, self.estimate, self.norm_adv
@@ -324,4 +330,11 @@ class FusedBatchTransforms(Transform):
             checks.append(("agent_info", "value", leaf, self._address(leaf)))
         if len(self._bound) > 256:
             self._bound.clear()
-        self._bound[(id(sample_tree), phases)] = (checks, graph)
+        direct = (None, 0, 0)
+        try:  # the instantiated graph's handle, when this torch exposes it
+            exec_ptr = int(graph.raw_cuda_graph_exec())
+            if exec_ptr and os.environ.get("PLB_DIRECT_GRAPH_LAUNCH", "1") == "1":
+                direct = (_lib.load().plb_graph_launch, exec_ptr, torch.cuda.current_device())
+        except Exception:
+            pass
+        self._bound[(id(sample_tree), phases)] = (checks, graph, direct)

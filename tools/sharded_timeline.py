@@ -42,13 +42,20 @@ if rank == 0:
     print(f"world {world}, PLB_TUNING={os.environ.get('PLB_TUNING', '')}: back-to-back graph replays, last step of 20 bursts (medians), us relative to the scan's start:")
     print("\n".join(gathered))
 torch.cuda.synchronize(); dist.barrier()
+import time
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
+h0 = time.perf_counter()
 for i in range(600):
     fz(trees[i % 6])
+h1 = time.perf_counter()
 e1.record(); torch.cuda.synchronize()
+host = torch.tensor([(h1 - h0) / 600 * 1e6], device=dev, dtype=torch.float64)
+allh = [torch.zeros_like(host) for _ in range(world)]
+dist.all_gather(allh, host)
 if rank == 0:
-    print(f"graph replay: {e0.elapsed_time(e1) / 600 * 1e3:.2f} us per step")
+    print(f"graph replay: {e0.elapsed_time(e1) / 600 * 1e3:.2f} us per step on the device; host time to ENQUEUE one step, per rank: "
+          + " ".join(f"{float(h):.1f}" for h in allh) + " us")
 lib.plb_debug_set_buffer(0)
 dist.barrier()
 os._exit(0)
