@@ -87,9 +87,7 @@ PLB_API int plb_sm_count(void);
  *           2 wherever the batch fits (also on one GPU)
  *   key 14 / 15: experiments on the resident kernel (1 = plain instead of cooperative launch / every thread polls)
  *   key 17: route of EstimateAdvantage + NormalizeAdvantage on a batch sharded over several GPUs: 0/3 last-CTA reduction +
- *           one record of partial sums per rank (default), 1 resident kernel, 2 two kernels + grid exchange
- *   key 18: record-per-rank consumer: 1 (default) one collector CTA reads the ranks' records and hands the result to the
- *           others through one tagged unit, 0 every CTA reads the records itself
+ *           one record of partial sums per rank (default), 1 resident kernel
  *   key 16: 1 = replay gather through the load/store-unit path only (default 0: TMA-staged rows of >= 128 B)
  *   key 13: 0 = index generation always by the single-CTA kernel (default 1: 8-CTA cluster kernel)
  * The environment variable PLB_TUNING="key=value,..." applies them when the Python package loads

@@ -210,54 +210,22 @@ normalize_advantage_partials_kernel(float *__restrict__ x, int64_t ld_x, int64_t
 // for all ranks' flags and merges in rank order in its prologue (warp 0), the first loads in flight.
 __global__ void __launch_bounds__(256)
 normalize_advantage_xch_kernel(float *__restrict__ x, int64_t ld_x, int64_t rows, int64_t cols, const XchRef xch,
-                               float eps, double *__restrict__ moments_out, unsigned long long *dbg, int collector)
+                               float eps, double *__restrict__ moments_out, unsigned long long *dbg)
 {
     __shared__ float s_mean, s_denom;
     if (dbg != nullptr && threadIdx.x == 0 && blockIdx.x == 0) dbg[4] = global_timer_ns();
-    // the wait comes first, on an idle memory pipe (see normalize_advantage_gx_kernel): polls queued behind the
-    // grid's first wave of streaming loads take microseconds each.
-    // collector != 0: only CTA 0 polls the ranks' records; it leaves (mean, denominator) as ONE epoch-tagged unit in
-    // the local buffer and every other CTA polls that unit with back-off -- with hundreds of CTAs x `world` lanes on
-    // the record lines, even records that had long arrived took 3.2 us to read at 8 ranks (1.3 us at 2)
-    const unsigned char *mine = xch.peers[xch.rank];
-    uint4 *result = reinterpret_cast<uint4 *>(const_cast<unsigned char *>(mine) + XCH_RESULT_BYTE);
-    if (collector == 0 || blockIdx.x == 0) {
-        if (threadIdx.x < 32) {
-            const Moments m = xch_wait_merge3(xch);
-            if (threadIdx.x == 0) {
-                if (dbg != nullptr && blockIdx.x == 0) dbg[5] = global_timer_ns();
-                const float mean = __double2float_rn(m.mean);
-                const float denom = __fadd_rn(__double2float_rn(sqrt(m.m2 / m.n)), eps);
-                s_mean = mean; s_denom = denom;
-                if (blockIdx.x == 0) {
-                    if (collector != 0) {
-                        const uint32_t epoch = *reinterpret_cast<const volatile uint32_t *>(mine);
-                        asm volatile("st.relaxed.sys.global.v4.u32 [%0], {%1, %2, %3, %4};"
-                                     ::"l"(result + (epoch & 1u)), "r"(__float_as_uint(mean)), "r"(epoch),
-                                       "r"(__float_as_uint(denom)), "r"(epoch) : "memory");
-                    }
-                    moments_out[0] = m.n; moments_out[1] = m.mean; moments_out[2] = m.m2;
-                }
+    // The wait comes first, on an idle memory pipe: a hop costs ~0.25 us there, but microseconds when the polls queue
+    // behind the ~10 MB of first-wave streaming loads of the grid (measured on the grid-exchange consumer that was
+    // tried in round 2: 3.3 us to read one word, 4.6 us for the records, with the loads issued first).
+    if (threadIdx.x < 32) {
+        const Moments m = xch_wait_merge3(xch);
+        if (threadIdx.x == 0) {
+            if (dbg != nullptr && blockIdx.x == 0) dbg[5] = global_timer_ns();
+            s_mean = __double2float_rn(m.mean);
+            s_denom = __fadd_rn(__double2float_rn(sqrt(m.m2 / m.n)), eps);
+            if (blockIdx.x == 0) {
+                moments_out[0] = m.n; moments_out[1] = m.mean; moments_out[2] = m.m2;
             }
-        }
-    } else if (threadIdx.x == 0) {
-        const long long t0 = clock64();
-        unsigned ns = 32;
-        while (true) {
-            const uint32_t epoch = *reinterpret_cast<const volatile uint32_t *>(mine);
-            uint4 q;
-            asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];"
-                         : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "l"(result + (epoch & 1u)) : "memory");
-            if (q.y == epoch && q.w == epoch && epoch != 0u) {
-                s_mean = __uint_as_float(q.x); s_denom = __uint_as_float(q.z);
-                break;
-            }
-            if (clock64() - t0 > 20000000000LL) {  // the collector never finished: poison instead of hanging
-                s_mean = __uint_as_float(0x7fc00000u); s_denom = 1.f;
-                break;
-            }
-            __nanosleep(ns);
-            if (ns < 256) ns <<= 1;
         }
     }
     __syncthreads();
@@ -295,130 +263,6 @@ normalize_advantage_xch_kernel(float *__restrict__ x, int64_t ld_x, int64_t rows
     if (dbg != nullptr && threadIdx.x == 0 && blockIdx.x == 0) dbg[6] = global_timer_ns();
 }
 
-// Consumer of the grid exchange on the two-kernel route: the advantage scan of every rank published one record
-// of partial sums per CTA into every rank's buffer (moments_tail with tail.gx).  CTA 0 is the collector: it waits
-// for the arrival hint, adds up all world x slots records in a fixed order (bit-identical on every rank) and
-// leaves (mean, denominator) as one epoch-tagged 16-byte unit in the local buffer header; every other CTA spins
-// on that single unit.  No serial tail in the producer, no NCCL, no host round trip; the last CTA out retires
-// the epoch.  The wait chain runs BEFORE any streaming load is issued: a hop costs ~0.25 us on an idle memory
-// pipe, but microseconds when it queues behind the ~10 MB of first-wave loads of the grid (measured: 3.3 us to
-// read the epoch word, 4.6 us for the records, with the loads issued first).
-// (minBlocksPerMultiprocessor = 4 caps the registers at 64: the collector path of CTA 0 spills a little, but the
-//  streaming CTAs keep the occupancy of the plain normalise kernel.)
-__global__ void __launch_bounds__(256, 4)
-normalize_advantage_gx_kernel(float *__restrict__ x, int64_t ld_x, int64_t rows, int64_t cols, const GridXch gx,
-                              float eps, double *__restrict__ moments_out, unsigned long long *dbg)
-{
-    __shared__ float s_mean, s_denom;
-    __shared__ Sums scratch[32];
-    __shared__ uint32_t s_epoch;
-    if (dbg != nullptr && threadIdx.x == 0 && blockIdx.x < 2) dbg[blockIdx.x * 8 + 0] = global_timer_ns();
-    if (threadIdx.x == 0) s_epoch = gx_epoch(gx);  // one load per CTA (hundreds of CTAs share the word's L2 line)
-    __syncthreads();
-    const uint32_t epoch = s_epoch;
-    unsigned char *mine = gx.self;
-    uint4 *result = reinterpret_cast<uint4 *>(mine + GX_RESULT_BYTE) + (epoch & 1u);  // {mean bits, epoch, denom bits, epoch}
-    if (blockIdx.x == 0) {
-        if (threadIdx.x == 0) {
-            if (dbg != nullptr) dbg[1] = global_timer_ns();
-            gx_wait_arrivals(gx, epoch);
-            if (dbg != nullptr) dbg[2] = global_timer_ns();
-        }
-        __syncthreads();
-        const Moments m = gx_collect(gx, epoch, scratch);
-        if (threadIdx.x == 0) {
-            if (dbg != nullptr) dbg[3] = global_timer_ns();
-            const float mean = __double2float_rn(m.mean);
-            const float denom = __fadd_rn(__double2float_rn(sqrt(m.m2 / m.n)), eps);
-            s_mean = mean; s_denom = denom;
-            asm volatile("st.relaxed.sys.global.v4.u32 [%0], {%1, %2, %3, %4};"
-                         ::"l"(result), "r"(__float_as_uint(mean)), "r"(epoch), "r"(__float_as_uint(denom)), "r"(epoch)
-                         : "memory");
-            moments_out[0] = m.n; moments_out[1] = m.mean; moments_out[2] = m.m2;
-            if (dbg != nullptr) dbg[4] = global_timer_ns();
-        }
-    } else if (threadIdx.x == 0) {
-        if (dbg != nullptr && blockIdx.x == 1) dbg[8 + 1] = global_timer_ns();
-        const long long t_start = clock64();
-        unsigned ns = 20;
-        while (true) {
-            uint4 q;
-            asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];"
-                         : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "l"(result) : "memory");
-            if (q.y == epoch && q.w == epoch) {
-                s_mean = __uint_as_float(q.x); s_denom = __uint_as_float(q.z);
-                break;
-            }
-            if (clock64() - t_start > 20000000000LL) {  // the collector never finished: flag it, poison the output
-                reinterpret_cast<volatile uint32_t *>(mine)[2] = 1u;
-                s_mean = __uint_as_float(0x7fc00000u); s_denom = 1.f;
-                break;
-            }
-            __nanosleep(ns);
-            if (ns < 160) ns <<= 1;
-        }
-    }
-    __syncthreads();
-    if (dbg != nullptr && threadIdx.x == 0 && blockIdx.x < 2) dbg[blockIdx.x * 8 + 5] = global_timer_ns();
-    const float mean = s_mean, denom = s_denom, rdenom = __frcp_rn(s_denom);
-    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
-    const int64_t vpr = cols >> 2;
-    const int64_t total = rows * vpr;
-    constexpr int U = 4;
-    for (int64_t base = tid; base < total; base += nthreads * U) {
-        float4 v[U];
-        int64_t off[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int64_t i = base + (int64_t)u * nthreads;
-            if (i < total) {
-                const int64_t r = (rows == 1) ? 0 : i / vpr;
-                off[u] = r * ld_x + ((i - r * vpr) << 2);
-                v[u] = *reinterpret_cast<const float4 *>(x + off[u]);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int64_t i = base + (int64_t)u * nthreads;
-            if (i < total) {
-                float4 o;
-                o.x = div_by(__fsub_rn(v[u].x, mean), denom, rdenom);
-                o.y = div_by(__fsub_rn(v[u].y, mean), denom, rdenom);
-                o.z = div_by(__fsub_rn(v[u].z, mean), denom, rdenom);
-                o.w = div_by(__fsub_rn(v[u].w, mean), denom, rdenom);
-                *reinterpret_cast<float4 *>(x + off[u]) = o;
-            }
-        }
-    }
-    if (threadIdx.x == 0) gx_retire(gx, epoch);  // off everybody's critical path: after this CTA's own stream
-    if (dbg != nullptr && threadIdx.x == 0 && blockIdx.x < 2) dbg[blockIdx.x * 8 + 7] = global_timer_ns();
-}
-
-// returns PLB_ERR_UNSUPPORTED when the region cannot take the 128-bit path
-int normalize_advantage_after_gx(float *x, int64_t ld_x, int64_t rows, int64_t cols, const GridXch &gx, double eps,
-                                 double *moments_out, cudaStream_t stream)
-{
-    if (rows * cols == 0) return PLB_OK;
-    if (ld_x == cols) {
-        cols = rows * cols;
-        rows = 1;
-        ld_x = cols;
-    }
-    if (!((cols % 4 == 0) && (ld_x % 4 == 0) && aligned(x, 16))) return PLB_ERR_UNSUPPORTED;
-    const int sms = sm_count();
-    PLB_REQUIRE(sms > 0, PLB_ERR_UNSUPPORTED, "no CUDA device");
-    int64_t blocks = ceil_div(rows * cols / 4, 256 * 4);
-    if (blocks < 1) blocks = 1;
-    if (blocks > (int64_t)sms * g_normadv_ctas_per_sm) blocks = (int64_t)sms * g_normadv_ctas_per_sm;
-    normalize_advantage_gx_kernel<<<(unsigned)blocks, 256, 0, stream>>>(x, ld_x, rows, cols, gx, (float)eps, moments_out,
-                                                                        debug_buffer());
-    PLB_LAUNCH_CHECK();
-    return PLB_OK;
-}
-
-
-
 int normalize_advantage_after_exchange(float *x, int64_t ld_x, int64_t rows, int64_t cols, const XchRef &xch, double eps,
                                        double *moments_out, cudaStream_t stream)
 {
@@ -435,7 +279,7 @@ int normalize_advantage_after_exchange(float *x, int64_t ld_x, int64_t rows, int
     if (blocks < 1) blocks = 1;
     if (blocks > (int64_t)sms * g_normadv_ctas_per_sm) blocks = (int64_t)sms * g_normadv_ctas_per_sm;
     normalize_advantage_xch_kernel<<<(unsigned)blocks, 256, 0, stream>>>(x, ld_x, rows, cols, xch, (float)eps, moments_out,
-                                                                         debug_buffer(), xch_collector());
+                                                                         debug_buffer());
     PLB_LAUNCH_CHECK();
     return PLB_OK;
 }

@@ -74,24 +74,20 @@ static int run_pipeline(const plb_batch_pipeline *d, int phases, cudaStream_t st
     gx.self = reinterpret_cast<unsigned char *>(d->gx_self);
     gx.rank = d->gx_rank; gx.world = d->gx_world; gx.slots = d->gx_slots;
     PLB_REQUIRE(gx.peers == nullptr || gx.self != nullptr, PLB_ERR_INVALID_ARGUMENT, "gx_peers without gx_self");
-    // sharded batches (gx.world > 1) have three routes for EstimateAdvantage + NormalizeAdvantage (key 17):
+    // sharded batches (gx.world > 1) have two routes for EstimateAdvantage + NormalizeAdvantage (tuning key 17):
     //   3 (auto)  last-CTA reduction in the scan, ONE record of partial sums per rank pushed to every rank, every CTA
     //             of the normalise kernel adds the `world` records up itself (xch_push3 / xch_wait_merge3);
-    //   1         the resident kernel (one launch; its write-only final phase runs at ~half of HBM speed);
-    //   2         two kernels + grid exchange: the scan's CTAs publish their partial sums to every rank as they
-    //             retire, a collector CTA of the normalise kernel adds them up and hands the result to the others
+    //   1         the resident kernel (one launch; its write-only final phase runs at ~half of HBM speed).
+    // (A third one -- per-CTA records + a collector CTA in the normalise kernel -- measured slower at every N and was
+    //  removed: DESIGN.md section 4.)
     const bool multi = gx.peers != nullptr && gx.world > 1;
-    const int route = sharded_route() == 0 ? 3 : sharded_route();
+    const int route = sharded_route() == 1 ? 1 : 3;
     const bool both_phases = est_adv && norm_adv && (phases & PLB_PHASE_B) && (phases & PLB_PHASE_C) && !split_partials;
     const bool want_resident = both_phases && gx.peers != nullptr && (plan & PLB_PLAN_RESIDENT) &&
                                (multi ? (route == 1 && plan != PLB_PLAN_AUTO) : resident_wanted(1));
-    const bool want_gx2 = both_phases && phases == PLB_PHASE_ALL && gx.peers != nullptr && (plan & PLB_PLAN_CHUNKED) &&
-                          ((multi && route == 2 && plan != PLB_PLAN_AUTO) ||
-                           (!multi && sharded_route() == 2 && !want_resident));  // one GPU: only when asked for (experiments)
-    bool adv_gx_published = false;
     // a sharded single-call chain must exchange the advantage statistics one way or another
     PLB_REQUIRE(!(both_phases && phases == PLB_PHASE_ALL && (multi || (d->xch_peers != nullptr && d->xch_world > 1))) ||
-                    want_resident || want_gx2 || (d->xch_peers != nullptr && d->xch_world > 1),
+                    want_resident || (d->xch_peers != nullptr && d->xch_world > 1),
                 PLB_ERR_INVALID_ARGUMENT, "sharded chain without an exchange route (plan %d, route %d)", plan, route);
     const bool update_in_tail = (phases == PLB_PHASE_ALL) && norm_rew && !use_xch;
     bool state_updated = false;
@@ -189,19 +185,12 @@ static int run_pipeline(const plb_batch_pipeline *d, int phases, cudaStream_t st
                 if (rc) return rc;
                 return PLB_OK;  // phases B and C are complete
             }
-            if (want_gx2) {  // partial sums travel through the grid-exchange records, not through the workspace
-                f.tail.gx = gx;
-                f.tail.partials_only = 0;
-                f.tail.xch.peers = nullptr;
-            }
             rc = scan_reverse(mode, d->reward, d->ld_reward, d->value, d->ld_value, d->done, d->ld_done,
                               d->bootstrap_value, d->advantage, d->ld_advantage, d->return_, d->ld_return,
                               T, B, 1, d->discount, d->gae_lambda, PLB_ALGO_CHUNKED,
                               (has_pre || norm_adv) ? &f : nullptr, stream);
-            if (rc == PLB_OK && want_gx2) adv_gx_published = true;
-            else if (rc == PLB_OK && norm_adv && direct_partials) adv_partials_published = true;
+            if (rc == PLB_OK && norm_adv && direct_partials) adv_partials_published = true;
             else if (rc == PLB_OK && norm_adv && use_xch) adv_pushed = true;
-            if (rc == PLB_ERR_UNSUPPORTED && want_gx2) return rc;  // agreed plan broken: never switch protocol alone
             if (rc == PLB_ERR_UNSUPPORTED && use_xch) return rc;
             if (rc == PLB_ERR_UNSUPPORTED) {  // unfused fallback, same results
                 if (has_pre) {
@@ -240,9 +229,6 @@ static int run_pipeline(const plb_batch_pipeline *d, int phases, cudaStream_t st
     }
 
     // ---------------------------------------------------------------- phase C
-    if ((phases & PLB_PHASE_C) && norm_adv && adv_gx_published)
-        return normalize_advantage_after_gx(d->advantage, d->ld_advantage, T, B, gx, d->eps_advantage,
-                                            d->advantage_moments, stream);
     if ((phases & PLB_PHASE_C) && norm_adv && adv_pushed) {
         rc = normalize_advantage_after_exchange(d->advantage, d->ld_advantage, T, B, xch, d->eps_advantage,
                                                 d->advantage_moments, stream);

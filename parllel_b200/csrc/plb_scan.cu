@@ -785,10 +785,8 @@ static int g_scan_max_stages = 0;     // experiments: cap on the input ring dept
 static int g_resident = 1;
 static int g_resident_plain_launch = 0;  // experiments: 1 = no cooperative-launch attribute (key 14)
 static int g_resident_poll = 0;          // experiments: 1 = every thread polls its own records (key 15)
-static int g_sharded_route = 0;          // sharded step: 0 auto, 1 resident kernel, 2 two kernels + grid exchange, 3 legacy (key 17)
+static int g_sharded_route = 0;          // sharded step: 0 / 3 one record per rank (default), 1 resident kernel (key 17)
 int sharded_route() { return g_sharded_route; }
-static int g_xch_collector = 1;          // record-per-rank consumer: 1 = one collector CTA + tagged result, 0 = every CTA polls (key 18)
-int xch_collector() { return g_xch_collector; }
 static unsigned long long *g_debug_buf = nullptr;  // plb_debug_set_buffer
 unsigned long long *debug_buffer() { return g_debug_buf; }
 
@@ -807,8 +805,6 @@ static int launch_chunked_inst(const chunked::TensorMaps &tm, chunked::Params p,
     // 228 KB of shared memory per SM, 1 KB reserved per CTA, ~1 KB of static scratch per CTA.
     int ctas_per_sm = p.n_strips <= sms ? 1 : (p.n_strips <= 2 * sms ? 2 : 3);
     if (NW > 8) ctas_per_sm = 1;
-    // statistics through the grid exchange: one record slot per CTA, so at most `slots` (= SM count) CTAs
-    if (p.tail.gx.peers != nullptr) ctas_per_sm = 1;
     auto kern = scan_pipelined_kernel<MODE, ACC, NW, R, HAS_PRE, HAS_STATS>;
     static thread_local size_t static_smem = ~(size_t)0;
     if (static_smem == ~(size_t)0) {
@@ -830,11 +826,7 @@ static int launch_chunked_inst(const chunked::TensorMaps &tm, chunked::Params p,
     PLB_REQUIRE(stages >= 1, PLB_ERR_UNSUPPORTED, "chunked scan does not fit in shared memory");
     p.n_stages = stages;
     const size_t smem = stage_bytes * stages + fixed_bytes;
-    int grid = p.n_strips < sms * ctas_per_sm ? p.n_strips : sms * ctas_per_sm;
-    if (p.tail.gx.peers != nullptr) {
-        if (grid > p.tail.gx.slots) grid = p.tail.gx.slots;
-        PLB_REQUIRE(grid >= 1, PLB_ERR_INVALID_ARGUMENT, "grid exchange without record slots");
-    }
+    const int grid = p.n_strips < sms * ctas_per_sm ? p.n_strips : sms * ctas_per_sm;
     static thread_local bool configured = false;
     if (!configured) {
         PLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
@@ -990,7 +982,7 @@ static int launch_chunked(const ChunkedIO &io, chunked::Params p, bool has_pre, 
         // few strips (<= one per SM) or many long strips (>= 4 per SM, T >= 256): one persistent CTA per SM
         // with 128-row tiles (C4: 49.8 us vs 55.0 us for 64-row tiles); in between: several CTAs per SM
         const int64_t strips = ceil_div(p.B, W);
-        geom = (strips <= sms || (strips >= 4 * (int64_t)sms && p.T >= 256) || p.tail.gx.peers != nullptr) ? 2 : 1;
+        geom = (strips <= sms || (strips >= 4 * (int64_t)sms && p.T >= 256)) ? 2 : 1;
     }
     if (p.T <= 64) geom = 1;
     const int TC = geom == 1 ? 64 : 128;
@@ -1190,7 +1182,6 @@ int plb_set_tuning(int key, int value)
         case 13: plb::set_rng_cluster(value); return PLB_OK;
         case 16: plb::set_gather_mode(value); return PLB_OK;
         case 17: plb::g_sharded_route = value; return PLB_OK;
-        case 18: plb::g_xch_collector = value; return PLB_OK;
         case 14: plb::g_resident_plain_launch = value; return PLB_OK;
         case 15: plb::g_resident_poll = value; return PLB_OK;
         case 5: plb::g_scan_debug = value; return PLB_OK;

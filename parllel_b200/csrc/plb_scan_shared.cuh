@@ -22,8 +22,7 @@ struct XchRef {
     unsigned char *const *peers;  // device array [world] of every rank's buffer, peer-mapped
     int rank, world;
 };
-constexpr size_t XCH_HEADER_BYTES = 1024;  // uint32 epoch @0, uint32 flags[2][world] @64, uint4 result[2] @768, data @1024
-constexpr size_t XCH_RESULT_BYTE = 768;    // {mean, epoch, denominator, epoch} by epoch parity: collector CTA -> the others
+constexpr size_t XCH_HEADER_BYTES = 1024;  // uint32 epoch @0, uint32 flags[2][world] @64, data @1024
 
 // Grid-wide + cross-GPU statistics exchange of the resident advantage kernel (one protocol for both):
 // every CTA of every rank stores its partial (count, mean, M2) as an epoch-tagged record straight into
@@ -35,9 +34,7 @@ constexpr size_t XCH_RESULT_BYTE = 768;    // {mean, epoch, denominator, epoch} 
 //  serialise in its L2 bank)
 //     line 0:  uint32 epoch @0 | uint32 status @8 (0 ok, 1 timed out)
 //     line 1:  uint32 exit_ticket @128
-//     line 2:  uint32 arrived[2] @256 | line 3:  uint4 result[2] @384     (see below)
-//     uint4 result[2] @384 (by epoch parity): {mean, epoch, denominator, epoch} left by the collector CTA of the
-//            two-kernel route for the other CTAs of its grid (local to the rank)
+//     line 2:  uint32 arrived[2] @256     (see below)
 //     uint32 arrived[2] @256 (by epoch parity): slots filled so far, a HINT for when to read -- the
 //            records validate themselves through their epoch tags, so no fence orders it after them
 //     records @512: [2 (epoch parity)][world][slots] x 64 B = 4 x {lo, epoch, hi, epoch} 16-byte units
@@ -49,7 +46,7 @@ struct GridXch {
     int slots;                    // records per rank and epoch (>= the largest grid of any rank)
 };
 constexpr size_t GX_HEADER_BYTES = 512;
-constexpr int GX_TICKET_WORD = 32, GX_ARRIVED_WORD = 64, GX_RESULT_BYTE = 384;  // header offsets (words / bytes)
+constexpr int GX_TICKET_WORD = 32, GX_ARRIVED_WORD = 64;  // header offsets in 32-bit words
 constexpr size_t GX_RECORD_BYTES = 64;
 constexpr int GX_RECORD_VALS = 4;
 constexpr int GX_MAX_WORLD = 32;
@@ -72,9 +69,6 @@ struct MomentsTail {
     // optional (multi-GPU): the finishing CTA pushes the final moments straight into every peer's
     // exchange buffer (NVLink P2P stores + release flags); the consumer kernel waits and merges
     XchRef xch;
-    // optional: instead of any local reduction, every CTA publishes its partial sums into the grid-exchange
-    // records of every rank (gx_publish); the consumer kernel collects them (normalize_advantage_after_gx)
-    GridXch gx;
     unsigned long long *dbg;  // experiments: %globaltimer stamps of the sharded step (plb_debug_set_buffer), or NULL
 };
 
@@ -88,7 +82,6 @@ static inline MomentsTail make_tail(double *moments_out, void *workspace)
     t.upd_mean = t.upd_var = t.upd_count = nullptr;
     t.upd_flags = 0;
     t.xch.peers = nullptr; t.xch.rank = 0; t.xch.world = 1;
-    t.gx.peers = nullptr; t.gx.self = nullptr; t.gx.rank = 0; t.gx.world = 1; t.gx.slots = 0;
     t.dbg = nullptr;
     return t;
 }
@@ -117,7 +110,6 @@ bool scan_chunked_supported(const float *reward, int64_t ld_r, const float *valu
                             const uint8_t *done, int64_t ld_d, int64_t T, int64_t B, int64_t inner);
 bool resident_wanted(int world);  // policy (plb_set_tuning key 12)
 int sharded_route();              // plb_set_tuning key 17
-int xch_collector();              // plb_set_tuning key 18
 unsigned long long *debug_buffer();  // plb_debug_set_buffer
 bool resident_supported(const float *reward, int64_t ld_r, const float *value, int64_t ld_v, const uint8_t *done,
                         int64_t ld_d, const float *adv, int64_t ld_a, const float *ret, int64_t ld_t,
@@ -160,8 +152,6 @@ int exchange_finish(const XchRef &xch, double *moments_out, double *upd_mean, do
                     int upd_flags, cudaStream_t stream);
 int normalize_advantage_after_exchange(float *x, int64_t ld_x, int64_t rows, int64_t cols, const XchRef &xch, double eps,
                                        double *moments_out, cudaStream_t stream);
-int normalize_advantage_after_gx(float *x, int64_t ld_x, int64_t rows, int64_t cols, const GridXch &gx, double eps,
-                                 double *moments_out, cudaStream_t stream);
 int normalize_advantage_from_partials(float *x, int64_t ld_x, int64_t rows, int64_t cols, void *tail_workspace,
                                       double eps, double *moments_out, cudaStream_t stream);
 int make_tensor_map_2d(CUtensorMap *tm, const void *base, int elem_bytes, int64_t rows, int64_t cols,
@@ -688,17 +678,6 @@ __device__ __forceinline__ void moments_tail(const Sums &mine, const MomentsTail
     __shared__ bool is_last;
     __syncthreads();  // scratch may have been used before
     const Sums blk = WARP_PIVOT ? block_reduce_sums_warp_pivot(mine, scratch) : block_reduce_sums(mine, scratch);
-    if (tail.gx.peers != nullptr) {
-        __shared__ double s_gx_pub[GX_RECORD_VALS];
-        __shared__ uint32_t s_gx_epoch;
-        if (threadIdx.x == 0) {
-            s_gx_pub[0] = blk.n; s_gx_pub[1] = blk.s1; s_gx_pub[2] = blk.s2; s_gx_pub[3] = blk.piv;
-            s_gx_epoch = gx_epoch(tail.gx);  // stays put until the CONSUMER kernel's last CTA retires the epoch
-        }
-        __syncthreads();
-        gx_publish(tail.gx, s_gx_epoch, s_gx_pub);
-        return;
-    }
     if (tail.partials_only) {
         if (threadIdx.x == 0) {
             tail.partials[blockIdx.x] = blk;

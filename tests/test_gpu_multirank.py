@@ -1,6 +1,7 @@
 """Multi-GPU parity on hardware: spawns one process per GPU (torchrun) running tests/multirank_worker.py,
 which checks every rank's shard against the CPU oracle evaluated on the GLOBAL batch, bit-identical
-statistics across ranks, NCCL route == in-kernel routes, and protocol agreement on uneven shards.
+statistics across ranks, NCCL route == in-kernel routes (record per rank, resident kernel), and protocol agreement
+on uneven shards.
 Skipped where fewer GPUs are visible; `gpurun --gpus N -- python -m pytest tests/test_gpu_multirank.py -m gpu`
 runs it, and the JSON reports it writes are kept under profiles/."""
 import os

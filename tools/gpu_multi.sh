@@ -10,12 +10,12 @@ for W in $WORLDS; do
   if [ $W -le $N ]; then
     timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $W --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $W --steps 1000 --warmup 10 > gpurun_out/bench_n${W}.json 2> gpurun_out/bench_n${W}.err; echo "bench N=$W rc=$?"
     tail -c 1500 gpurun_out/bench_n${W}.json; tail -5 gpurun_out/bench_n${W}.err
-    for R in 1 2; do
+    for R in 1; do
       PLB_TUNING=17=$R timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $W --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $W --steps 500 --warmup 10 --windows 3 > gpurun_out/bench_n${W}_route$R.json 2> gpurun_out/bench_n${W}_route$R.err; echo "bench N=$W route $R rc=$?"
     done
     python - <<PY
 import json
-for tag in ("", "_route1", "_route2"):
+for tag in ("", "_route1"):
     try:
         for line in open("gpurun_out/bench_n${W}%s.json" % tag):
             if line.startswith("{"):

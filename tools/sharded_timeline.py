@@ -21,7 +21,8 @@ for item in filter(None, os.environ.get("PLB_TUNING", "").split(",")):
     pass  # applied by _lib.load()
 buf = torch.zeros(64, dtype=torch.int64, device=dev)
 lib.plb_debug_set_buffer(buf.data_ptr())  # set BEFORE capture: the pointer is a launch argument baked into the graphs
-fz = FusedBatchTransforms([EstimateAdvantage(0.99, 0.95), NormalizeAdvantage(trees[0])])
+fz = FusedBatchTransforms([EstimateAdvantage(0.99, 0.95), NormalizeAdvantage(trees[0])],
+                          use_cuda_graph=os.environ.get("PLB_EAGER", "0") != "1")
 for i in range(30):
     fz(trees[i % 6])
 torch.cuda.synchronize(); dist.barrier()
@@ -54,7 +55,7 @@ host = torch.tensor([(h1 - h0) / 600 * 1e6], device=dev, dtype=torch.float64)
 allh = [torch.zeros_like(host) for _ in range(world)]
 dist.all_gather(allh, host)
 if rank == 0:
-    print(f"graph replay: {e0.elapsed_time(e1) / 600 * 1e3:.2f} us per step on the device; host time to ENQUEUE one step, per rank: "
+    print(f"{'eager launches' if os.environ.get('PLB_EAGER', '0') == '1' else 'graph replay'}: {e0.elapsed_time(e1) / 600 * 1e3:.2f} us per step on the device; host time to ENQUEUE one step, per rank: "
           + " ".join(f"{float(h):.1f}" for h in allh) + " us")
 lib.plb_debug_set_buffer(0)
 dist.barrier()
