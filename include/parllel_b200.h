@@ -76,10 +76,10 @@ PLB_API int plb_sm_count(void);
 /* Tuning / diagnostics knobs (process-wide; used by tools/ and the tests, not by the transforms).
  *   key 0: tile geometry of the chunked scan: 0 auto, 1 = 8 warps x 8 rows, 2 = 8 warps x 16 rows
  *   key 3: NormalizeObservations step kernel: 0 auto (4, then 1, then 2, then three kernels),
- *          1 shared-memory slab through TMA, 2 two-pass L2 slab, 3 two-CTA cluster slab,
+ *          1 shared-memory slab through TMA, 2 two-pass L2 slab,
  *          4 shared-memory slab through cp.async / direct stores
  *   key 5: experiments only: 1 skip the fused statistics, 2 skip their tail (results then incomplete),
- *          4 resident kernel: final advantage through plain stores instead of per-warp TMA stores
+ *          4 resident kernel: final advantage through plain stores instead of TMA stores
  *   key 7: slab width of observation variant 4: 8, 16 (default) or 32 columns
  *   key 9: cap on the input ring depth of the chunked scan (0 = as many stages as fit)
  *   key 11: grid cap of the streaming normalise kernels, CTAs of 256 threads per SM (default 4)

@@ -488,7 +488,7 @@ int plb_normalize_observations_step_f32(float *obs, int64_t ld_obs, int64_t rows
     // streamed twice with the second pass served by L2
     {
         // measured at C2 (B = 1024, F = 21168): shared-memory slab filled by cp.async / drained by 128-bit
-        // stores 39.5 us, the same slab through TMA 42.5 us, two-CTA cluster slab 53.9 us, two-pass L2 slab
+        // stores 39.5 us, the same slab through TMA 42.5 us, two-CTA cluster slab 53.9 us (removed), two-pass L2 slab
         // 55 us, three kernels 85 us -> prefer the load/store-unit slab, then TMA (no cols % 4 requirement),
         // then the L2 variant when the slab is too tall for shared memory
         int rc1 = PLB_ERR_UNSUPPORTED;
@@ -496,9 +496,6 @@ int plb_normalize_observations_step_f32(float *obs, int64_t ld_obs, int64_t rows
         if (variant == 4 || variant == 0)
             rc1 = obs_step_lsu(obs, ld_obs, rows, cols, row_valid, mean, var, count, batch_count,
                                eps, flags, clip_lo, clip_hi, stream);
-        if (variant == 3)
-            rc1 = obs_step_cluster(obs, ld_obs, rows, cols, row_valid, mean, var, count, batch_count,
-                                   eps, flags, clip_lo, clip_hi, stream);
         if (rc1 == PLB_ERR_UNSUPPORTED && variant != 2)
             rc1 = obs_step_single_pass(obs, ld_obs, rows, cols, row_valid, mean, var, count, batch_count,
                                        eps, flags, clip_lo, clip_hi, stream);

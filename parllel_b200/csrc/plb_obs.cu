@@ -2,10 +2,9 @@
 //   stats.update(obs[valid]); obs[:] = (obs - stats.mean) / sqrt(stats.var + eps)
 // for one [B, F] float32 step with per-feature running statistics (float64).
 //
-// Four designs live here; plb_norm.cu picks (default: variant D, then A, then B, then three kernels):
+// Three designs live here; plb_norm.cu picks (default: variant D, then A, then B, then three kernels):
 //   A  obs::obs_step_kernel            shared-memory slab, TMA in / TMA out
 //   B  obs_l2::obs_step_l2_kernel      two passes over a 256-byte-wide slab, second one served by L2
-//   C  obs_cl::obs_step_cluster_kernel 32-column slab split by rows over a two-CTA cluster (DSMEM)
 //   D  obs_lsu::obs_step_lsu_kernel    shared-memory slab, cp.async in / 128-bit global stores out
 //
 // Variant A.  Each CTA owns a [B rows x 16 columns] slab: TMA brings the whole slab into shared memory once,
@@ -360,274 +359,8 @@ obs_step_l2_kernel(const Params p)
 
 }  // namespace obs_l2
 
-// ---------------------------------------------------------------------------------------------
-// Variant C: a [rows x 32 columns] slab shared by a cluster of two CTAs, split by rows.
-// 128-byte row segments instead of 64 (the TMA unit moves ~20 % more per second at that width)
-// at the same 64 KB of shared memory per CTA for B = 1024, so three CTAs still share an SM.  Each
-// CTA reduces the moments of its half; the two halves swap their 32 per-column sums through
-// distributed shared memory (st.shared::cluster) around one cluster barrier and both derive the
-// same updated statistics (rank-0 half first, then rank 1); rank 0 writes the running state.
-// ---------------------------------------------------------------------------------------------
-namespace obs_cl {
-
-constexpr int FC = 32;                 // columns per slab: 128-byte row segments, one warp per row
-constexpr int THREADS = 256;
-constexpr int GROUPS = THREADS / FC;   // 8 row groups; thread (g, c) takes rows g, g+8, ... of its half
-
-struct Params {
-    int64_t rows, cols;
-    int half;                 // rows per CTA (rows == 2 * half)
-    int box_rows, n_boxes;    // half == box_rows * n_boxes
-    const uint8_t *row_valid;
-    double *mean, *var;
-    const double *count;
-    double *batch_count_out;
-    double eps;
-    float clip_lo, clip_hi;
-    int flags;
-    int n_slabs;
-};
-
-__device__ __forceinline__ uint32_t cluster_ctarank()
-{
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void cluster_sync_all()
-{
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void st_peer_f64x2(void *local_smem, uint32_t peer, double a, double b)
-{
-    const uint32_t laddr = (uint32_t)__cvta_generic_to_shared(local_smem);
-    uint32_t raddr;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(laddr), "r"(peer));
-    asm volatile("st.shared::cluster.v2.f64 [%0], {%1, %2};" ::"r"(raddr), "d"(a), "d"(b) : "memory");
-}
-
-__global__ void __launch_bounds__(THREADS)
-obs_step_cluster_kernel(const __grid_constant__ CUtensorMap tm, const Params p)
-{
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    float (*slab)[FC] = reinterpret_cast<float (*)[FC]>(smem_raw);  // [half][FC]
-    __shared__ unsigned long long full;
-    __shared__ Sums part[GROUPS][FC];
-    __shared__ __align__(16) Sums xbuf[2][2][FC];  // [slab parity][cluster rank][column]
-    __shared__ double col_mean[FC], col_inv[FC];
-
-    const int c = threadIdx.x % FC, g = threadIdx.x / FC;
-    const uint32_t rank = cluster_ctarank();
-    const int pair = (int)(blockIdx.x >> 1), n_pairs = (int)(gridDim.x >> 1);
-    const int nrows = p.half;
-    const int row0 = (int)rank * p.half;
-    const uint32_t slab_tx = (uint32_t)p.half * FC * sizeof(float);
-    const int my_n = (p.n_slabs - pair + n_pairs - 1) / n_pairs;
-
-    auto load_slab = [&](int j) {  // thread 0 only
-        const int c0 = (pair + j * n_pairs) * FC;
-        mbar_arrive_expect_tx(&full, slab_tx);
-        for (int bx = 0; bx < p.n_boxes; ++bx)
-            tma_load_2d(&slab[bx * p.box_rows][0], &tm, c0, row0 + bx * p.box_rows, &full);
-    };
-
-    if (threadIdx.x == 0) {
-        mbar_init(&full, 1);
-        fence_proxy_async_smem();
-        tma_prefetch_desc(&tm);
-        if (my_n > 0) load_slab(0);
-    }
-    __syncthreads();
-    cluster_sync_all();  // the peer CTA is running: its shared memory may be written from here on
-
-    const double cnt = p.count[0];
-    for (int i = 0; i < my_n; ++i) {
-        const uint32_t parity = (uint32_t)(i & 1);
-        const int s = pair + i * n_pairs;
-        const int c0 = s * FC;
-        const bool col_ok = (int64_t)c0 + c < p.cols;
-        const double old_mean = (g == 0 && col_ok) ? p.mean[c0 + c] : 0.0;   // overlaps the load
-        const double old_var = (g == 0 && col_ok) ? p.var[c0 + c] : 1.0;
-        mbar_wait(&full, parity);
-
-        // ---- moments of this CTA's half of the slab ------------------------------------------
-        const float piv = slab[g][c];
-        double S1 = 0.0, S2 = 0.0;
-        unsigned n_acc = 0;
-        if (p.row_valid == nullptr) {
-            int r0 = g;
-            for (; r0 + 15 * GROUPS < nrows; r0 += GROUPS * 16) {
-                float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
-#pragma unroll
-                for (int k = 0; k < 16; k += 2) {
-                    const float d0 = slab[r0 + k * GROUPS][c] - piv, d1 = slab[r0 + (k + 1) * GROUPS][c] - piv;
-                    s1a += d0; s1b += d1;
-                    s2a = fmaf(d0, d0, s2a); s2b = fmaf(d1, d1, s2b);
-                }
-                S1 += (double)(s1a + s1b);
-                S2 += (double)(s2a + s2b);
-                n_acc += 16;
-            }
-            float s1 = 0.f, s2 = 0.f;
-            for (int r = r0; r < nrows; r += GROUPS) {
-                const float d = slab[r][c] - piv;
-                s1 += d;
-                s2 = fmaf(d, d, s2);
-                ++n_acc;
-            }
-            S1 += (double)s1;
-            S2 += (double)s2;
-        } else {
-            for (int r0 = g; r0 < nrows; r0 += GROUPS * 16) {
-                float s1 = 0.f, s2 = 0.f;
-#pragma unroll 4
-                for (int k = 0; k < 16; ++k) {
-                    const int r = r0 + k * GROUPS;
-                    if (r < nrows && p.row_valid[row0 + r] != 0) {
-                        const float d = slab[r][c] - piv;
-                        s1 += d;
-                        s2 = fmaf(d, d, s2);
-                        ++n_acc;
-                    }
-                }
-                S1 += (double)s1;
-                S2 += (double)s2;
-            }
-        }
-        Sums mine;
-        mine.n = (double)n_acc; mine.s1 = S1; mine.s2 = S2; mine.piv = (double)piv;
-        part[g][c] = mine;
-        __syncthreads();
-        if (g == 0) {
-            Sums tot = part[0][c];
-            for (int k = 1; k < GROUPS; ++k) {
-                Sums q = part[k][c];
-                if (q.n > 0.0) {
-                    if (tot.n == 0.0) tot = q;
-                    else {
-                        q = rebase(q, tot.piv);
-                        tot.n += q.n; tot.s1 += q.s1; tot.s2 += q.s2;
-                    }
-                }
-            }
-            Sums *slot = &xbuf[parity][rank][c];
-            *slot = tot;
-            st_peer_f64x2(&slot->n, rank ^ 1u, tot.n, tot.s1);      // Sums = {n, s1, s2, piv}
-            st_peer_f64x2(&slot->s2, rank ^ 1u, tot.s2, tot.piv);
-        }
-        cluster_sync_all();  // both halves' sums are in both CTAs' xbuf[parity]
-        if (g == 0) {
-            Sums tot = xbuf[parity][0][c];
-            Sums q = xbuf[parity][1][c];
-            if (q.n > 0.0) {
-                if (tot.n == 0.0) tot = q;
-                else {
-                    q = rebase(q, tot.piv);
-                    tot.n += q.n; tot.s1 += q.s1; tot.s2 += q.s2;
-                }
-            }
-            const Moments m = to_moments(tot);
-            double mean = old_mean, var = old_var;
-            chan_update_scalar(m.n, m.mean, m.m2, cnt, p.flags, mean, var);
-            if (col_ok && rank == 0) {
-                p.mean[c0 + c] = mean;
-                p.var[c0 + c] = var;
-            }
-            col_mean[c] = mean;
-            col_inv[c] = 1.0 / sqrt(__dadd_rn(var, p.eps));
-            if (s == 0 && c == 0 && rank == 0) p.batch_count_out[0] = m.n;
-        }
-        __syncthreads();
-
-        // ---- normalise this half in place (float32 hi+lo constants, see obs_step_kernel) ------
-        const double mu = col_mean[c], inv = col_inv[c];
-        const float mu_hi = __double2float_rn(mu), mu_lo = __double2float_rn(mu - (double)mu_hi);
-        const float inv_hi = __double2float_rn(inv), inv_lo = __double2float_rn(inv - (double)inv_hi);
-#pragma unroll 8
-        for (int r = g; r < nrows; r += GROUPS) {
-            const float d = (slab[r][c] - mu_hi) - mu_lo;
-            slab[r][c] = fminf(fmaxf(fmaf(d, inv_hi, d * inv_lo), p.clip_lo), p.clip_hi);
-        }
-        fence_proxy_async_smem();
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            for (int bx = 0; bx < p.n_boxes; ++bx)
-                tma_store_2d(&tm, &slab[bx * p.box_rows][0], c0, row0 + bx * p.box_rows);
-            tma_store_commit();
-            if (i + 1 < my_n) {
-                tma_store_wait_read<0>();
-                load_slab(i + 1);
-            }
-        }
-    }
-    if (threadIdx.x == 0) tma_store_wait<0>();
-    cluster_sync_all();  // no CTA retires while its peer may still address its shared memory
-}
-
-}  // namespace obs_cl
-
-// Returns PLB_ERR_UNSUPPORTED when the shape does not fit (odd row count, half-slab without a usable
-// box height, slab too tall for shared memory).
-int obs_step_cluster(float *x, int64_t ld, int64_t rows, int64_t cols, const uint8_t *row_valid,
-                     double *mean, double *var, const double *count, double *batch_count_out,
-                     double eps, int flags, float clip_lo, float clip_hi, cudaStream_t stream)
-{
-    using namespace obs_cl;
-    if (!(aligned(x, 16) && ld % 4 == 0) || rows < 128 || rows % 2 != 0 || rows > (int64_t)INT32_MAX / 2 ||
-        cols > (int64_t)INT32_MAX / 2 || cols < 2 * FC)
-        return PLB_ERR_UNSUPPORTED;
-    const int half = (int)(rows / 2);
-    int box_rows = 0;  // largest divisor of `half` that fits a TMA box (exact boxes: stores must not spill into the peer's half)
-    for (int b = half < 256 ? half : 256; b >= 32; --b)
-        if (half % b == 0) { box_rows = b; break; }
-    if (box_rows == 0) return PLB_ERR_UNSUPPORTED;
-    const size_t slab_bytes = (size_t)half * FC * sizeof(float);
-    static thread_local size_t static_bytes = 0;
-    if (static_bytes == 0) {
-        cudaFuncAttributes attr;
-        PLB_CUDA(cudaFuncGetAttributes(&attr, obs_step_cluster_kernel));
-        static_bytes = attr.sharedSizeBytes;
-    }
-    const size_t avail = 227 * 1024 - static_bytes;
-    if (slab_bytes > avail) return PLB_ERR_UNSUPPORTED;
-    CUtensorMap tm;
-    int rc = make_tensor_map_2d(&tm, x, 4, rows, cols, ld, box_rows, FC);
-    if (rc) return rc;
-    const int sms = sm_count();
-    PLB_REQUIRE(sms > 0, PLB_ERR_UNSUPPORTED, "no CUDA device");
-    Params p = {};
-    p.rows = rows; p.cols = cols;
-    p.half = half; p.box_rows = box_rows; p.n_boxes = half / box_rows;
-    p.row_valid = row_valid;
-    p.mean = mean; p.var = var; p.count = count;
-    p.batch_count_out = batch_count_out;
-    p.eps = eps; p.flags = flags;
-    p.clip_lo = clip_lo; p.clip_hi = clip_hi;
-    p.n_slabs = (int)ceil_div(cols, FC);
-    int ctas_per_sm = (int)((228 * 1024) / (slab_bytes + static_bytes + 1024));
-    if (ctas_per_sm < 1) ctas_per_sm = 1;
-    if (ctas_per_sm > 4) ctas_per_sm = 4;
-    int pairs = sms * ctas_per_sm / 2;
-    if (pairs > p.n_slabs) pairs = p.n_slabs;
-    static thread_local bool configured = false;
-    if (!configured) {
-        PLB_CUDA(cudaFuncSetAttribute(obs_step_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)avail));
-        configured = true;
-    }
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2u * (unsigned)pairs);
-    cfg.blockDim = dim3(THREADS);
-    cfg.dynamicSmemBytes = slab_bytes;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    PLB_CUDA(cudaLaunchKernelEx(&cfg, obs_step_cluster_kernel, tm, p));
-    PLB_LAUNCH_CHECK();
-    return PLB_OK;
-}
+// (Variant C of round 1 -- a [rows x 32 columns] slab split by rows over a two-CTA cluster with a DSMEM exchange of the
+//  per-column sums -- measured 53.9 us at C2 against 39.5 us for variant D and was removed in round 2.)
 
 // ---------------------------------------------------------------------------------------------
 // Variant D: the shared-memory slab of variant A filled and drained by the load/store units instead

@@ -141,9 +141,6 @@ int obs_step_two_pass_l2(float *x, int64_t ld, int64_t rows, int64_t cols, const
 int obs_step_lsu(float *x, int64_t ld, int64_t rows, int64_t cols, const uint8_t *row_valid,
                  double *mean, double *var, const double *count, double *batch_count_out,
                  double eps, int flags, float clip_lo, float clip_hi, cudaStream_t stream);
-int obs_step_cluster(float *x, int64_t ld, int64_t rows, int64_t cols, const uint8_t *row_valid,
-                     double *mean, double *var, const double *count, double *batch_count_out,
-                     double eps, int flags, float clip_lo, float clip_hi, cudaStream_t stream);
 int obs_step_single_pass(float *x, int64_t ld, int64_t rows, int64_t cols, const uint8_t *row_valid,
                          double *mean, double *var, const double *count, double *batch_count_out,
                          double eps, int flags, float clip_lo, float clip_hi, cudaStream_t stream);

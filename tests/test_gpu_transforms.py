@@ -366,7 +366,7 @@ def test_c2_shape_observation_step_vs_oracle():
     np.testing.assert_allclose(tf.obs_statistics.var, stats.var, rtol=5e-6)
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 4])
+@pytest.mark.parametrize("variant", [1, 2, 4])
 @pytest.mark.parametrize("B,F,masked", [(64, 192, False), (300, 52, True), (4100, 64, False), (17, 8, True),
                                         (1024, 200, False), (256, 100, True), (1000, 64, False)])
 def test_observation_step_kernel_variants_vs_oracle(variant, B, F, masked):
@@ -418,7 +418,7 @@ def test_observation_clip_extension():
     for t in range(2):
         O.normalize_observations_step(ref[t], stats)
     ref = np.clip(ref, -1.5, 1.5)
-    for variant in (0, 1, 2, 3, 4):
+    for variant in (0, 1, 2, 4):
         _lib.load().plb_set_tuning(3, variant)
         d = torch.from_numpy(obs).cuda()
         NormalizeObservations({"observation": d}, obs_shape=(40,), initial_count=10, clip=1.5).normalize_batch(d)
@@ -575,7 +575,7 @@ def test_c2_full_size_observation_step_properties():
         count = total
         expect.append(((x - mean) / torch.sqrt(var + 1e-6)).to(torch.float32))
     results = {}
-    for variant in (1, 2, 3, 4):
+    for variant in (1, 2, 4):
         _lib.load().plb_set_tuning(3, variant)
         try:
             d = obs.clone()
@@ -592,5 +592,4 @@ def test_c2_full_size_observation_step_properties():
             assert err <= 1e-5, (variant, t, err)
         results[variant] = d
     assert (results[1] - results[2]).abs().max().item() <= 2e-6
-    assert (results[1] - results[3]).abs().max().item() <= 2e-6
     assert (results[1] - results[4]).abs().max().item() <= 2e-6
