@@ -20,7 +20,7 @@ HEADERS = ["plb_common.cuh", "plb_scan_shared.cuh", os.path.join("..", "..", "in
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
-    "-O3", "-std=c++17", "-lineinfo",
+    "-O3", "-std=c++17", "-lineinfo", "--threads", "0",
     "-Xcompiler", "-fPIC,-fvisibility=hidden,-O3",
     "-Xptxas", "-v",
     "--expt-relaxed-constexpr", "--extended-lambda",

@@ -22,6 +22,10 @@ void count_launch(int resident)
     if (resident) __atomic_add_fetch(&g_resident_launches, 1, __ATOMIC_RELAXED);
 }
 
+static int g_pdl = 1;
+int pdl_enabled() { return g_pdl; }
+void set_pdl_enabled(int on) { g_pdl = on ? 1 : 0; }
+
 int sm_count()
 {
     static thread_local int cached_dev = -1;

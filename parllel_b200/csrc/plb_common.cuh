@@ -46,6 +46,15 @@ void count_launch(int resident);
 
 int sm_count();  // cached per device
 
+// Programmatic dependent launch (plb_set_tuning key 18, default on).  The streaming kernels of the batch chain are
+// launched with cudaLaunchAttributeProgrammaticStreamSerialization: every CTA signals `launch_dependents` on entry, so
+// the NEXT kernel of the stream is scheduled, runs its prologue (barrier init, descriptor prefetch) and parks in
+// `griddepcontrol.wait` while this one is still streaming -- the ~2 us launch gap at each kernel boundary is hidden.
+// Rule for every kernel launched this way: ALL threads execute griddep_wait() before their first global access and
+// before any early return (the completion of a grid must imply the completion of its predecessor).
+int pdl_enabled();
+void set_pdl_enabled(int on);
+
 static inline bool aligned(const void *p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
@@ -128,6 +137,27 @@ struct PivotAcc {
 };
 
 #ifdef __CUDACC__
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// <<<grid, block, smem, stream>>> with the programmatic-serialization attribute (when enabled)
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                     Args &&...args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // Block-wide reduction of per-thread Sums without divisions: agree on a pivot (the pivot of the
 // lowest-numbered thread that saw data), rebase, add.  Result valid in thread 0.
 // `scratch` needs >= 32 Sums; all threads of the block must call.

@@ -146,6 +146,8 @@ normalize_advantage_partials_kernel(float *__restrict__ x, int64_t ld_x, int64_t
                                     float eps, double *__restrict__ moments_out)
 {
     __shared__ float s_mean, s_denom;
+    griddep_launch_dependents();
+    griddep_wait();  // the scan that produced x and the partials has completed
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
     const int64_t vpr = cols >> 2;
@@ -213,6 +215,8 @@ normalize_advantage_xch_kernel(float *__restrict__ x, int64_t ld_x, int64_t rows
                                float eps, double *__restrict__ moments_out, unsigned long long *dbg)
 {
     __shared__ float s_mean, s_denom;
+    griddep_launch_dependents();
+    griddep_wait();  // this rank's scan (x, the epoch word) has completed; the peers' records are polled below
     if (dbg != nullptr && threadIdx.x == 0 && blockIdx.x == 0) dbg[4] = global_timer_ns();
     // The wait comes first, on an idle memory pipe: a hop costs ~0.25 us there, but microseconds when the polls queue
     // behind the ~10 MB of first-wave streaming loads of the grid (measured on the grid-exchange consumer that was
@@ -278,8 +282,8 @@ int normalize_advantage_after_exchange(float *x, int64_t ld_x, int64_t rows, int
     int64_t blocks = ceil_div(rows * cols / 4, 256 * 4);
     if (blocks < 1) blocks = 1;
     if (blocks > (int64_t)sms * g_normadv_ctas_per_sm) blocks = (int64_t)sms * g_normadv_ctas_per_sm;
-    normalize_advantage_xch_kernel<<<(unsigned)blocks, 256, 0, stream>>>(x, ld_x, rows, cols, xch, (float)eps, moments_out,
-                                                                         debug_buffer());
+    PLB_CUDA(launch_pdl(normalize_advantage_xch_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, x, ld_x, rows, cols, xch,
+                        (float)eps, moments_out, debug_buffer()));
     PLB_LAUNCH_CHECK();
     return PLB_OK;
 }
@@ -301,9 +305,8 @@ int normalize_advantage_from_partials(float *x, int64_t ld_x, int64_t rows, int6
     if (blocks < 1) blocks = 1;
     if (blocks > (int64_t)sms * g_normadv_ctas_per_sm) blocks = (int64_t)sms * g_normadv_ctas_per_sm;
     const MomentsTail t = make_tail(moments_out, tail_workspace);
-    // (programmatic dependent launch of this kernel behind the scan was measured: no gain, 22.3 us either way)
-    normalize_advantage_partials_kernel<<<(unsigned)blocks, 256, 0, stream>>>(x, ld_x, rows, cols, t.partials,
-                                                                              t.ticket + 1, (float)eps, moments_out);
+    PLB_CUDA(launch_pdl(normalize_advantage_partials_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, x, ld_x, rows, cols,
+                        t.partials, t.ticket + 1, (float)eps, moments_out));
     PLB_LAUNCH_CHECK();
     return PLB_OK;
 }

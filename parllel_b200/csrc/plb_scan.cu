@@ -289,6 +289,10 @@ scan_pipelined_kernel(const __grid_constant__ TensorMaps tm, const Params p)
 
     __shared__ uint32_t s_tmem_base, s_epoch;
     __shared__ unsigned char *s_peers[GX_MAX_WORLD];
+    // programmatic dependent launch: the next kernel of the stream may be scheduled from here on (it parks in its own
+    // griddepcontrol.wait until this grid has completed); this grid's shared-memory prologue overlaps its predecessor
+    griddep_launch_dependents();
+    if (RESIDENT) griddep_wait();
     if (RESIDENT) gx_preload_peers(p.gx, s_peers);
     if (RESIDENT && p.dbg != nullptr && threadIdx.x == 0) p.dbg[blockIdx.x * 8 + 0] = global_timer_ns();
     if (!RESIDENT && HAS_STATS && p.tail.dbg != nullptr && threadIdx.x == 0 && blockIdx.x == 0) p.tail.dbg[0] = global_timer_ns();
@@ -304,6 +308,7 @@ scan_pipelined_kernel(const __grid_constant__ TensorMaps tm, const Params p)
         }
         tmem_fence_before_sync();
     }
+    if (!RESIDENT) griddep_wait();  // everything below reads or writes global memory the predecessor may own
     __syncthreads();
     uint32_t tmem_warp = 0;  // this warp's lane quarter and column half of tile 0
     if (RESIDENT) {
@@ -832,7 +837,7 @@ static int launch_chunked_inst(const chunked::TensorMaps &tm, chunked::Params p,
         PLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
         configured = true;
     }
-    kern<<<grid, NW * 32, smem, stream>>>(tm, p);
+    PLB_CUDA(launch_pdl(kern, dim3(grid), dim3(NW * 32), smem, stream, tm, p));
     PLB_LAUNCH_CHECK();
     return PLB_OK;
 }
@@ -1184,6 +1189,7 @@ int plb_set_tuning(int key, int value)
         case 17: plb::g_sharded_route = value; return PLB_OK;
         case 14: plb::g_resident_plain_launch = value; return PLB_OK;
         case 15: plb::g_resident_poll = value; return PLB_OK;
+        case 18: plb::set_pdl_enabled(value); return PLB_OK;
         case 5: plb::g_scan_debug = value; return PLB_OK;
         case 9: plb::g_scan_max_stages = value; return PLB_OK;
         case 11: plb::set_normadv_ctas_per_sm(value); return PLB_OK;

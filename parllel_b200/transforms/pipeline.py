@@ -38,7 +38,17 @@ _ORDER = (NormalizeRewards, ClipRewards, EstimateAdvantage, NormalizeAdvantage)
 
 
 class FusedBatchTransforms(Transform):
-    def __init__(self, transforms, use_cuda_graph: bool = True, group=None) -> None:
+    def __init__(self, transforms, use_cuda_graph: bool = True, group=None, launch: str | None = None) -> None:
+        # how a step on device-resident leaves reaches the GPU once its leaves are known:
+        #   "direct": the cached descriptor goes straight to plb_batch_pipeline_f32 -- the kernels are launched with
+        #             programmatic dependent launch, so consecutive kernels (and consecutive steps) overlap their
+        #             launch latency and prologues with the predecessor's tail;
+        #   "graph":  the launch sequence is captured into a CUDA graph per set of leaf addresses and replayed
+        #             (a graph-to-graph boundary is a full serialisation: measured ~3 us per step slower at C1).
+        launch = launch or os.environ.get("PLB_LAUNCH", "direct")
+        if launch not in ("direct", "graph"):
+            raise ValueError("launch must be 'direct' or 'graph'")
+        self.launch = launch if use_cuda_graph else "eager"
         self.transforms = list(transforms)
         self.norm_rewards = self.clip = self.estimate = self.norm_adv = None
         slot = -1
@@ -149,16 +159,21 @@ class FusedBatchTransforms(Transform):
         # inside somebody else's stream capture the launches are enqueued as they are (no nested graphs)
         if self._bound:
             entry = self._bound.get((id(sample_tree), phases))
-            if entry is not None and self._still_bound(sample_tree, entry[0]) \
-                    and not torch._C._cuda_isCurrentStreamCapturing():
-                launch, exec_ptr, dev_index = entry[2]
-                if launch is not None:  # cudaGraphLaunch through the C ABI on the caller's current stream
-                    rc = launch(exec_ptr, torch._C._cuda_getCurrentRawStream(dev_index))
+            if entry is not None and self._still_bound(sample_tree, entry[0]):
+                launch, handle, dev_index = entry[2]
+                if entry[1] is None:  # direct: the cached descriptor, on the caller's current stream (capturable)
+                    rc = launch(handle, phases, torch._C._cuda_getCurrentRawStream(dev_index))
                     if rc:
-                        _lib.check(rc, "plb_graph_launch")
-                else:
-                    entry[1].replay()
-                return sample_tree
+                        _lib.check(rc, "fused transforms")
+                    return sample_tree
+                if not torch._C._cuda_isCurrentStreamCapturing():
+                    if launch is not None:  # cudaGraphLaunch through the C ABI on the caller's current stream
+                        rc = launch(handle, torch._C._cuda_getCurrentRawStream(dev_index))
+                        if rc:
+                            _lib.check(rc, "plb_graph_launch")
+                    else:
+                        entry[1].replay()
+                    return sample_tree
         capturing = torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()
         nr, est, na = self.norm_rewards, self.estimate, self.norm_adv
         lib = _lib.load()
@@ -272,9 +287,13 @@ class FusedBatchTransforms(Transform):
                 keep.append(ex)
                 in_kernel_exchange = True
 
+        split_phases = distributed and phases == _lib.PHASE_ALL and not in_kernel_exchange
+        carry_copies = nr is not None and T > 0 and not (d.carry_return_out and d.carry_done_out) \
+            and (nr._carry_return is not None or nr._carry_done is not None)
+
         def enqueue():
             s = stream_ptr(dev)
-            if distributed and phases == _lib.PHASE_ALL and not in_kernel_exchange:
+            if split_phases:
                 _lib.check(lib.plb_batch_pipeline_f32(ctypes.byref(d), _lib.PHASE_A, s), "fused transforms (A)")
                 if nr is not None:
                     self._exchange(self._moments[0:3])
@@ -284,7 +303,7 @@ class FusedBatchTransforms(Transform):
                 _lib.check(lib.plb_batch_pipeline_f32(ctypes.byref(d), _lib.PHASE_C, s), "fused transforms (C)")
             else:
                 _lib.check(lib.plb_batch_pipeline_f32(ctypes.byref(d), phases, s), "fused transforms")
-            if nr is not None and T > 0 and not (d.carry_return_out and d.carry_done_out):
+            if carry_copies:
                 if nr._carry_return is not None:
                     nr._carry_return.copy_(past[T - 1])
                 if nr._carry_done is not None:
@@ -292,7 +311,10 @@ class FusedBatchTransforms(Transform):
 
         # the NCCL all-gathers of the sharded chain are captured into the graph as well
         graphable = self.use_cuda_graph and not st.staged and not capturing
-        if not graphable:
+        if self.launch == "direct" and self.use_cuda_graph and not st.staged and not split_phases and not carry_copies:
+            enqueue()
+            self._bind_direct(sample_tree, phases, d, keep, dev)
+        elif not graphable:
             enqueue()
         else:
             key = bytes(d) + bytes([phases])
@@ -314,22 +336,39 @@ class FusedBatchTransforms(Transform):
         st.finish()
         return sample_tree
 
-    def _bind(self, sample_tree, phases: int, graph) -> None:
-        """Remember the graph for this tree object together with the device leaves it was captured for."""
+    def _leaf_checks(self, sample_tree):
+        """(name, sub-name, leaf object, address) of every device leaf the chain may touch; None if one is on the host."""
         checks = []
         for name in self._LEAF_NAMES:
             if name in sample_tree:
                 leaf = sample_tree[name]
                 if self._leaf_signature(leaf) is None:
-                    return  # host leaf: never replayed
+                    return None  # host leaf: never replayed
                 checks.append((name, None, leaf, self._address(leaf)))
         if "agent_info" in sample_tree and "value" in sample_tree["agent_info"]:
             leaf = sample_tree["agent_info"]["value"]
             if self._leaf_signature(leaf) is None:
-                return
+                return None
             checks.append(("agent_info", "value", leaf, self._address(leaf)))
         if len(self._bound) > 256:
             self._bound.clear()
+        return checks
+
+    def _bind_direct(self, sample_tree, phases: int, d, keep, dev) -> None:
+        """Remember the filled descriptor for this tree object: while its leaves stay the same objects at the same
+        addresses, a call is one C call (the descriptor holds raw device pointers; `keep` and the transforms'
+        own buffers keep the auxiliary memory alive)."""
+        checks = self._leaf_checks(sample_tree)
+        if checks is None:
+            return
+        self._bound[(id(sample_tree), phases)] = (checks, None, (_lib.load().plb_batch_pipeline_f32, ctypes.byref(d), dev.index),
+                                                  (d, keep))
+
+    def _bind(self, sample_tree, phases: int, graph) -> None:
+        """Remember the graph for this tree object together with the device leaves it was captured for."""
+        checks = self._leaf_checks(sample_tree)
+        if checks is None:
+            return
         direct = (None, 0, 0)
         try:  # the instantiated graph's handle, when this torch exposes it
             exec_ptr = int(graph.raw_cuda_graph_exec())

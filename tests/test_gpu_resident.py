@@ -46,9 +46,9 @@ def _oracle_step(batch, gamma, lam, valid=None):
     return adv, ret
 
 
-def _fused(tree, lam, graph=False):
+def _fused(tree, lam, graph=False, launch=None):
     from parllel_b200.transforms import EstimateAdvantage, FusedBatchTransforms, NormalizeAdvantage
-    return FusedBatchTransforms([EstimateAdvantage(0.99, lam), NormalizeAdvantage(tree)], use_cuda_graph=graph)
+    return FusedBatchTransforms([EstimateAdvantage(0.99, lam), NormalizeAdvantage(tree)], use_cuda_graph=graph, launch=launch)
 
 
 # (T, B): one tile; ragged T below / above one tile; T <= 64 (64-row tiles); many strips; a ragged last
@@ -122,15 +122,16 @@ def test_resident_with_valid_mask_vs_oracle():
     assert_within_tolerance(tree["return_"].cpu().numpy(), ret_ref, what="masked return_")
 
 
-def test_resident_replays_through_a_graph_and_epochs_advance():
-    """Many launches on one buffer set (eager, captured, replayed): every launch must see only its own
-    epoch's records.  Inputs change between launches, so a stale record would show."""
+@pytest.mark.parametrize("launch", ["graph", "direct"])
+def test_resident_replays_through_a_graph_and_epochs_advance(launch):
+    """Many launches on one buffer set (eager, captured, replayed -- or the bound descriptor launched directly):
+    every launch must see only its own epoch's records.  Inputs change between launches, so a stale record would show."""
     from parllel_b200 import _lib
     T, B = 256, 2048
     rng = np.random.default_rng(5)
     batch = make_batch(rng, T, B, 0.01)
     tree = _tree(batch)
-    fused = _fused(tree, 0.95, graph=True)
+    fused = _fused(tree, 0.95, graph=True, launch=launch)
     for it in range(7):
         scale = np.float32(1.0 + it)
         cur = dict(batch, reward=batch["reward"] * scale)
@@ -142,12 +143,13 @@ def test_resident_replays_through_a_graph_and_epochs_advance():
     assert fused._gx is not None and fused._gx.status() == 0
 
 
-def test_swapping_a_leaf_in_the_same_tree_does_not_replay_a_stale_graph():
+@pytest.mark.parametrize("launch", ["graph", "direct"])
+def test_swapping_a_leaf_in_the_same_tree_does_not_replay_a_stale_graph(launch):
     """the replay fast path must look at the leaves the tree holds NOW."""
     T, B = 128, 256
     batch = make_batch(np.random.default_rng(9), T, B, 0.01)
     tree = _tree(batch)
-    fused = _fused(tree, 0.95, graph=True)
+    fused = _fused(tree, 0.95, graph=True, launch=launch)
     for _ in range(4):  # eager, capture, bound replays
         fused(tree)
     other = dict(batch, reward=batch["reward"] * np.float32(3.0))

@@ -71,9 +71,11 @@ def test_batch_transform_pipeline_matches_reference(golden, name, leaves):
 
 @pytest.mark.parametrize("name", ["pipeline_c0", "pipeline_valid", "pipeline_lambda1"])
 @pytest.mark.parametrize("leaves", ["device_array", "plain_tensor", "host_numpy"])
-@pytest.mark.parametrize("graph", [False, True])
-def test_fused_batch_transforms_match_reference(golden, name, leaves, graph):
-    """The same chain through FusedBatchTransforms (one C call, optional CUDA graph replay)."""
+@pytest.mark.parametrize("mode", ["eager", "graph", "direct"])
+def test_fused_batch_transforms_match_reference(golden, name, leaves, mode):
+    """The same chain through FusedBatchTransforms (one C call; rebuilt every call, replayed as a CUDA graph, or
+    the cached descriptor launched directly with programmatic dependent launch)."""
+    graph = mode != "eager"
     from parllel_b200 import ArrayDict
     from parllel_b200.transforms import (ClipRewards, EstimateAdvantage, FusedBatchTransforms, NormalizeAdvantage,
                                          NormalizeRewards)
@@ -91,7 +93,7 @@ def test_fused_batch_transforms_match_reference(golden, name, leaves, graph):
         ClipRewards(reward_min=clip_lo, reward_max=clip_hi),
         EstimateAdvantage(discount=0.99, gae_lambda=lam),
         NormalizeAdvantage(tree),
-    ], use_cuda_graph=graph)
+    ], use_cuda_graph=graph, launch=mode if graph else None)
     reps = 3 if (graph and leaves == "plain_tensor") else 1  # replays must not depend on stale state
     for it in range(int(n_batches)):
         if leaves == "device_array":
