@@ -62,6 +62,8 @@ elementwise_kernel(float *__restrict__ x, int64_t ld_x, int64_t rows, int64_t co
 // 22.0 with 8, 22.4 with 2); plb_set_tuning key 11
 static int g_normadv_ctas_per_sm = 4;
 void set_normadv_ctas_per_sm(int v) { g_normadv_ctas_per_sm = v > 0 ? v : 4; }
+static int g_normadv_xch_threads = 1024;  // CTA size of the sharded normalise kernel (plb_set_tuning key 20)
+void set_normadv_xch_threads(int v) { g_normadv_xch_threads = (v == 256 || v == 512 || v == 1024) ? v : 1024; }
 
 template <class F>
 static int launch_elementwise(float *x, int64_t ld_x, int64_t rows, int64_t cols, bool col_dependent, F f,
@@ -210,7 +212,9 @@ normalize_advantage_partials_kernel(float *__restrict__ x, int64_t ld_x, int64_t
 
 // Multi-GPU variant: the producer's tail pushed this rank's moments to every peer; each CTA waits
 // for all ranks' flags and merges in rank order in its prologue (warp 0), the first loads in flight.
-__global__ void __launch_bounds__(256)
+// CTAs of up to 1024 threads, one per SM: every CTA's first warp reads the same few record lines, and with four
+// 256-thread CTAs per SM those reads alone serialised in L2 for ~3 us at eight ranks (plb_set_tuning key 20).
+__global__ void __launch_bounds__(1024)
 normalize_advantage_xch_kernel(float *__restrict__ x, int64_t ld_x, int64_t rows, int64_t cols, const XchRef xch,
                                float eps, double *__restrict__ moments_out, unsigned long long *dbg)
 {
@@ -279,10 +283,12 @@ int normalize_advantage_after_exchange(float *x, int64_t ld_x, int64_t rows, int
     if (!((cols % 4 == 0) && (ld_x % 4 == 0) && aligned(x, 16))) return PLB_ERR_UNSUPPORTED;
     const int sms = sm_count();
     PLB_REQUIRE(sms > 0, PLB_ERR_UNSUPPORTED, "no CUDA device");
-    int64_t blocks = ceil_div(rows * cols / 4, 256 * 4);
+    const int threads = g_normadv_xch_threads;
+    const int ctas_per_sm = (256 * g_normadv_ctas_per_sm + threads - 1) / threads;  // same threads per SM as the one-GPU kernel
+    int64_t blocks = ceil_div(rows * cols / 4, (int64_t)threads * 4);
     if (blocks < 1) blocks = 1;
-    if (blocks > (int64_t)sms * g_normadv_ctas_per_sm) blocks = (int64_t)sms * g_normadv_ctas_per_sm;
-    PLB_CUDA(launch_pdl(normalize_advantage_xch_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, x, ld_x, rows, cols, xch,
+    if (blocks > (int64_t)sms * ctas_per_sm) blocks = (int64_t)sms * ctas_per_sm;
+    PLB_CUDA(launch_pdl(normalize_advantage_xch_kernel, dim3((unsigned)blocks), dim3(threads), 0, stream, x, ld_x, rows, cols, xch,
                         (float)eps, moments_out, debug_buffer()));
     PLB_LAUNCH_CHECK();
     return PLB_OK;

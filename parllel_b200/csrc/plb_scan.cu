@@ -1190,6 +1190,7 @@ int plb_set_tuning(int key, int value)
         case 14: plb::g_resident_plain_launch = value; return PLB_OK;
         case 15: plb::g_resident_poll = value; return PLB_OK;
         case 18: plb::set_pdl_enabled(value); return PLB_OK;
+        case 20: plb::set_normadv_xch_threads(value); return PLB_OK;
         case 5: plb::g_scan_debug = value; return PLB_OK;
         case 9: plb::g_scan_max_stages = value; return PLB_OK;
         case 11: plb::set_normadv_ctas_per_sm(value); return PLB_OK;

@@ -132,6 +132,7 @@ int column_moments(const float *x, int64_t ld_x, int64_t rows, int64_t cols, con
 int obs_variant();
 void set_obs_variant(int v);
 void set_normadv_ctas_per_sm(int v);
+void set_normadv_xch_threads(int v);
 void set_obs_lsu_cols(int v);
 void set_rng_cluster(int v);
 void set_gather_mode(int v);
@@ -301,6 +302,7 @@ __device__ __forceinline__ void xch_push3(const XchRef &x, Sums mine_sums)
 {
     const int lane = threadIdx.x & 31;
     unsigned char *mine = x.peers[x.rank];
+    unsigned char *peer = lane < x.world ? x.peers[lane] : nullptr;  // in flight together with the epoch round trip
     uint32_t epoch = 0;
     if (lane == 0) {
         uint32_t *ep = reinterpret_cast<uint32_t *>(mine);
@@ -313,7 +315,7 @@ __device__ __forceinline__ void xch_push3(const XchRef &x, Sums mine_sums)
     for (int i = 0; i < 4; ++i) vals[i] = __shfl_sync(0xffffffffu, vals[i], 0);
     const int par = (int)(epoch & 1u);
     if (lane < x.world) {
-        uint2 *dst = reinterpret_cast<uint2 *>(x.peers[lane] + xch_ll_offset(x.world)) +
+        uint2 *dst = reinterpret_cast<uint2 *>(peer + xch_ll_offset(x.world)) +
                      ((size_t)par * x.world + x.rank) * 8;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
