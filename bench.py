@@ -429,7 +429,7 @@ def measure_secondary(dev, peak, with_cpu):
         chain(tree)
     torch.cuda.synchronize()
     e2e["full_chain_T128_B16"] = {"us_per_call_wall": (time.perf_counter() - t0) / n * 1e6, "bound": "launch latency",
-                                  "api": "FusedBatchTransforms(4 transforms)(tree), CUDA-graph replay, device leaves"}
+                                  "api": "FusedBatchTransforms(4 transforms)(tree), bound descriptor + programmatic dependent launch, device leaves"}
     # ---- the reference's own CPU code for the same calls (host cores of this box)
     if with_cpu:
         try:
@@ -538,7 +538,7 @@ def main():
     n_sets = max(3, int(np.ceil(2.2 * L2_BYTES / set_bytes)))
     sets = [_device_tree(synth_batch(1000 * rank + i + 1), dev) for i in range(n_sets)]
 
-    # the public API: the sampler's batch_transforms list, fused (one C call, CUDA-graph replay)
+    # the public API: the sampler's batch_transforms list, fused (one C call per step on the bound descriptor)
     fused = FusedBatchTransforms([EstimateAdvantage(GAMMA, LAMBDA), NormalizeAdvantage(sets[0])])
 
     def step(i):
@@ -722,7 +722,7 @@ def main():
                 "api": "HostBatchPipeline(FusedBatchTransforms([EstimateAdvantage, NormalizeAdvantage])).submit(tree)/wait() on pinned numpy trees, 2 slots"},
         "gpu_launches": args.steps * kernels_per_step,
         "kernels_per_step": kernels_per_step,
-        "kernels_per_step_source": "plb_launch_counters() around one eager step (the timed steps replay its captured graph)",
+        "kernels_per_step_source": "plb_launch_counters() around one step (every timed step is one plb_batch_pipeline_f32 call on the cached descriptor; its kernels are launched with programmatic dependent launch)",
         "roofline": {"bound": "hbm", "kernel": kernel_name,
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "peak_source": peak_src, "traffic": traffic, "traffic_source": traffic_src,

@@ -216,6 +216,8 @@ extern "C" int plb_gather_tree(const plb_gather_leaf *leaves, int32_t n_leaves, 
                                       GATHER_TMA_WARPS * GATHER_TILE_BYTES));
         configured = true;
     }
+    // (programmatic dependent launch measured here: back-to-back gathers of n = 16 384 went from 5.1 to 6.4 us -- the
+    //  early-scheduled CTAs of the next launch hold shared memory the TMA role wants -- so this stays a plain launch)
     gather_tree_kernel<<<(unsigned)blocks, GATHER_THREADS, smem, (cudaStream_t)stream>>>(p);
     PLB_LAUNCH_CHECK();
     return PLB_OK;

@@ -427,6 +427,8 @@ replay_indices_cluster_kernel(const RngParams p, const StreamSpec sp)
     __shared__ unsigned long long s_reject[2];  // first rejected word of the round, this CTA (by round parity)
     __shared__ long long s_first;               // ... of the whole cluster
     __shared__ u128 s_base;                     // generator state at output index pos >> 1 (after a restart)
+    griddep_launch_dependents();
+    griddep_wait();  // the generator state is whatever the previous draw left
     cg::cluster_group cluster = cg::this_cluster();
     const int cta = (int)cluster.block_rank();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -612,6 +614,8 @@ __global__ void __launch_bounds__(RNG_THREADS)
 replay_indices_kernel(const RngParams p)
 {
     __shared__ RngShared sh;
+    griddep_launch_dependents();
+    griddep_wait();
     if (threadIdx.x == 0) {
         sh.state = ((u128)p.state[0] << 64) | (u128)p.state[1];
         sh.inc = ((u128)p.state[2] << 64) | (u128)p.state[3];
@@ -703,9 +707,9 @@ extern "C" int plb_replay_sample_indices(uint64_t *pcg64_state, int64_t size_T, 
     sp.add = full ? cursor + oldest_invalid : 0;
     sp.mod = full ? size_T : 0;
     if (rare && g_rng_cluster) {
-        replay_indices_cluster_kernel<<<CL_CTAS, RNG_THREADS, 0, (cudaStream_t)stream>>>(p, sp);
+        PLB_CUDA(launch_pdl(replay_indices_cluster_kernel, dim3(CL_CTAS), dim3(RNG_THREADS), 0, (cudaStream_t)stream, p, sp));
     } else {
-        replay_indices_kernel<<<1, RNG_THREADS, 0, (cudaStream_t)stream>>>(p);
+        PLB_CUDA(launch_pdl(replay_indices_kernel, dim3(1), dim3(RNG_THREADS), 0, (cudaStream_t)stream, p));
     }
     PLB_LAUNCH_CHECK();
     return PLB_OK;
