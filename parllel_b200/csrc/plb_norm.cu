@@ -62,6 +62,8 @@ elementwise_kernel(float *__restrict__ x, int64_t ld_x, int64_t rows, int64_t co
 // 22.0 with 8, 22.4 with 2); plb_set_tuning key 11
 static int g_normadv_ctas_per_sm = 4;
 void set_normadv_ctas_per_sm(int v) { g_normadv_ctas_per_sm = v > 0 ? v : 4; }
+static int g_normadv_reduce_mode = 0;     // experiments: 1 = serial partial loads in the normalise prologue (key 21)
+void set_normadv_reduce_mode(int v) { g_normadv_reduce_mode = v; }
 static int g_normadv_xch_threads = 1024;  // CTA size of the sharded normalise kernel (plb_set_tuning key 20)
 void set_normadv_xch_threads(int v) { g_normadv_xch_threads = (v == 256 || v == 512 || v == 1024) ? v : 1024; }
 
@@ -142,10 +144,13 @@ struct NormColsOp {
 // NormalizeAdvantage tail fed directly by the partial Sums the advantage scan published: each CTA
 // reduces the (<= few hundred) partials itself while its first loads are in flight, so the scan needs
 // no serial last-CTA epilogue.  CTA 0 also writes the final (count, mean, M2) for API consumers.
-__global__ void __launch_bounds__(256)
+// CONTIG (dense [T, B] leaves, seen as one row): no per-element row arithmetic.  (Capping it at 32 registers so that
+// four of these CTAs fit next to a resident scan CTA spilled the first batch of loads: not kept.)
+template <bool CONTIG>
+__global__ void __launch_bounds__(256, 4)
 normalize_advantage_partials_kernel(float *__restrict__ x, int64_t ld_x, int64_t rows, int64_t cols,
                                     const Sums *__restrict__ partials, const unsigned *__restrict__ n_partials,
-                                    float eps, double *__restrict__ moments_out)
+                                    float eps, double *__restrict__ moments_out, int reduce_mode)
 {
     __shared__ float s_mean, s_denom;
     griddep_launch_dependents();
@@ -155,24 +160,21 @@ normalize_advantage_partials_kernel(float *__restrict__ x, int64_t ld_x, int64_t
     const int64_t vpr = cols >> 2;
     const int64_t total = rows * vpr;
     constexpr int U = 4;
+    auto offset_of = [&](int64_t i) -> int64_t {
+        if (CONTIG) return i << 2;
+        const int64_t r = (rows == 1) ? 0 : i / vpr;
+        return r * ld_x + ((i - r * vpr) << 2);
+    };
     // first batch of loads before the reduction, so the two overlap
     float4 v[U];
-    int64_t off[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
         const int64_t i = tid + (int64_t)u * nthreads;
-        if (i < total) {
-            const int64_t r = (rows == 1) ? 0 : i / vpr;
-            off[u] = r * ld_x + ((i - r * vpr) << 2);
-        }
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-        const int64_t i = tid + (int64_t)u * nthreads;
-        if (i < total) v[u] = *reinterpret_cast<const float4 *>(x + off[u]);
+        if (i < total) v[u] = *reinterpret_cast<const float4 *>(x + offset_of(i));
     }
     if (threadIdx.x < 32) {  // one warp reduces the partial sums; the others go straight to the barrier
-        const Moments m = reduce_published_partials_warp(partials, *n_partials);
+        const Moments m = reduce_mode == 1 ? reduce_published_partials_warp_serial(partials, *n_partials)
+                                            : reduce_published_partials_warp(partials, n_partials);
         if (threadIdx.x == 0) {
             s_mean = __double2float_rn(m.mean);
             s_denom = __fadd_rn(__double2float_rn(sqrt(m.m2 / m.n)), eps);
@@ -188,11 +190,7 @@ normalize_advantage_partials_kernel(float *__restrict__ x, int64_t ld_x, int64_t
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int64_t i = base + (int64_t)u * nthreads;
-                if (i < total) {
-                    const int64_t r = (rows == 1) ? 0 : i / vpr;
-                    off[u] = r * ld_x + ((i - r * vpr) << 2);
-                    v[u] = *reinterpret_cast<const float4 *>(x + off[u]);
-                }
+                if (i < total) v[u] = *reinterpret_cast<const float4 *>(x + offset_of(i));
             }
         }
 #pragma unroll
@@ -204,7 +202,7 @@ normalize_advantage_partials_kernel(float *__restrict__ x, int64_t ld_x, int64_t
                 o.y = div_by(__fsub_rn(v[u].y, mean), denom, rdenom);
                 o.z = div_by(__fsub_rn(v[u].z, mean), denom, rdenom);
                 o.w = div_by(__fsub_rn(v[u].w, mean), denom, rdenom);
-                *reinterpret_cast<float4 *>(x + off[u]) = o;
+                *reinterpret_cast<float4 *>(x + offset_of(i)) = o;
             }
         }
     }
@@ -311,8 +309,12 @@ int normalize_advantage_from_partials(float *x, int64_t ld_x, int64_t rows, int6
     if (blocks < 1) blocks = 1;
     if (blocks > (int64_t)sms * g_normadv_ctas_per_sm) blocks = (int64_t)sms * g_normadv_ctas_per_sm;
     const MomentsTail t = make_tail(moments_out, tail_workspace);
-    PLB_CUDA(launch_pdl(normalize_advantage_partials_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, x, ld_x, rows, cols,
-                        t.partials, t.ticket + 1, (float)eps, moments_out));
+    if (rows == 1)
+        PLB_CUDA(launch_pdl(normalize_advantage_partials_kernel<true>, dim3((unsigned)blocks), dim3(256), 0, stream, x, ld_x, rows,
+                            cols, t.partials, t.ticket + 1, (float)eps, moments_out, g_normadv_reduce_mode));
+    else
+        PLB_CUDA(launch_pdl(normalize_advantage_partials_kernel<false>, dim3((unsigned)blocks), dim3(256), 0, stream, x, ld_x, rows,
+                            cols, t.partials, t.ticket + 1, (float)eps, moments_out, g_normadv_reduce_mode));
     PLB_LAUNCH_CHECK();
     return PLB_OK;
 }

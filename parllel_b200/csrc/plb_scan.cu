@@ -308,6 +308,12 @@ scan_pipelined_kernel(const __grid_constant__ TensorMaps tm, const Params p)
         }
         tmem_fence_before_sync();
     }
+    // the tensor maps are kernel parameters: their fetch can run ahead of the predecessor's completion
+    if (!RESIDENT && threadIdx.x == 0) {
+        tma_prefetch_desc(&tm.r);
+        if (REVERSE) tma_prefetch_desc(&tm.v);
+        tma_prefetch_desc(&tm.d);
+    }
     if (!RESIDENT) griddep_wait();  // everything below reads or writes global memory the predecessor may own
     __syncthreads();
     uint32_t tmem_warp = 0;  // this warp's lane quarter and column half of tile 0
@@ -351,9 +357,11 @@ scan_pipelined_kernel(const __grid_constant__ TensorMaps tm, const Params p)
         tma_store_commit();
     };
     if (threadIdx.x == 0) {
-        tma_prefetch_desc(&tm.r);
-        if (REVERSE) tma_prefetch_desc(&tm.v);
-        tma_prefetch_desc(&tm.d);
+        if (RESIDENT) {
+            tma_prefetch_desc(&tm.r);
+            if (REVERSE) tma_prefetch_desc(&tm.v);
+            tma_prefetch_desc(&tm.d);
+        }
         for (int s = 0; s < n_stages && iss_strip < n_strips; ++s) issue_one();
         if (!RESIDENT) tma_prefetch_desc(&tm.o0);
         if (REVERSE) tma_prefetch_desc(&tm.o1);
@@ -1191,6 +1199,7 @@ int plb_set_tuning(int key, int value)
         case 15: plb::g_resident_poll = value; return PLB_OK;
         case 18: plb::set_pdl_enabled(value); return PLB_OK;
         case 20: plb::set_normadv_xch_threads(value); return PLB_OK;
+        case 21: plb::set_normadv_reduce_mode(value); return PLB_OK;
         case 5: plb::g_scan_debug = value; return PLB_OK;
         case 9: plb::g_scan_max_stages = value; return PLB_OK;
         case 11: plb::set_normadv_ctas_per_sm(value); return PLB_OK;

@@ -133,6 +133,7 @@ int obs_variant();
 void set_obs_variant(int v);
 void set_normadv_ctas_per_sm(int v);
 void set_normadv_xch_threads(int v);
+void set_normadv_reduce_mode(int v);
 void set_obs_lsu_cols(int v);
 void set_rng_cluster(int v);
 void set_gather_mode(int v);
@@ -764,7 +765,63 @@ __device__ __forceinline__ Moments reduce_published_partials(const Sums *partial
 // Same reduction by ONE warp (no block barrier inside): lanes take partials lane, lane+32, ... in index
 // order, rebase onto the first non-empty pivot of the warp, then plain shuffle adds.  Every lane returns
 // the same moments; summation order depends only on n.
-__device__ __forceinline__ Moments reduce_published_partials_warp(const Sums *partials, unsigned n)
+// The count and the first four partials of every lane are fetched in ONE round trip (slots beyond the count exist --
+// the workspace holds MOMENTS_MAX_PARTIALS of them -- and are masked afterwards): the seven other warps of the CTA
+// sit at a barrier until this returns, and a chain of dependent L2 loads (count, then partial after partial) was 40 %
+// of the normalise kernel's stall samples.
+__device__ __forceinline__ Moments reduce_published_partials_warp(const Sums *partials, const unsigned *n_partials)
+{
+    static_assert(MOMENTS_MAX_PARTIALS >= 128, "the first four partials per lane are fetched before their count is known");
+    const unsigned lane = threadIdx.x & 31u;
+    Sums q[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const double2 *src = reinterpret_cast<const double2 *>(partials + lane + 32u * k);
+        const double2 lo = __ldcg(src), hi = __ldcg(src + 1);
+        q[k].n = lo.x; q[k].s1 = lo.y; q[k].s2 = hi.x; q[k].piv = hi.y;
+    }
+    const unsigned n = __ldcg(n_partials);
+    Sums acc;
+    acc.n = 0.0; acc.s1 = 0.0; acc.s2 = 0.0; acc.piv = 0.0;
+    for (unsigned base = lane;; base += 128u) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (base + 32u * k < n && q[k].n > 0.0) {
+                if (acc.n == 0.0) acc = q[k];
+                else {
+                    const Sums r = rebase(q[k], acc.piv);
+                    acc.n += r.n; acc.s1 += r.s1; acc.s2 += r.s2;
+                }
+            }
+        }
+        if (base + 128u >= n) break;  // (uniform enough: lanes beyond n just carry empty sums)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const unsigned i = base + 128u + 32u * k;
+            if (i < n) {
+                const double2 *src = reinterpret_cast<const double2 *>(partials + i);
+                const double2 lo = __ldcg(src), hi = __ldcg(src + 1);
+                q[k].n = lo.x; q[k].s1 = lo.y; q[k].s2 = hi.x; q[k].piv = hi.y;
+            } else {
+                q[k].n = 0.0;
+            }
+        }
+    }
+    const unsigned has = __ballot_sync(0xffffffffu, acc.n > 0.0);
+    const int src_lane = has ? (__ffs(has) - 1) : 0;
+    const double P = __shfl_sync(0xffffffffu, acc.piv, src_lane);
+    acc = rebase(acc, P);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        acc.n += __shfl_xor_sync(0xffffffffu, acc.n, d);
+        acc.s1 += __shfl_xor_sync(0xffffffffu, acc.s1, d);
+        acc.s2 += __shfl_xor_sync(0xffffffffu, acc.s2, d);
+    }
+    acc.piv = P;
+    return to_moments(acc);
+}
+// (experiments, plb_set_tuning key 21 = 1: the round-2 loop, count first, then one partial after the other)
+__device__ __forceinline__ Moments reduce_published_partials_warp_serial(const Sums *partials, unsigned n)
 {
     const unsigned lane = threadIdx.x & 31u;
     Sums acc;

@@ -49,24 +49,9 @@ def measure(name, call, n=3000):
           f"p50 {np.percentile(per, 50):6.2f}  p90 {np.percentile(per, 90):6.2f}  p99 {np.percentile(per, 99):6.2f}  max {per.max():8.2f} us", flush=True)
 
 
-measure("fused(tree) [graph fast path]", lambda i: fz(trees[i % N_SETS]))
-measure("fused(tree) [direct, PDL on]", lambda i: fd(trees[i % N_SETS]))
-lib.plb_set_tuning(18, 0)
-measure("fused(tree) [direct, PDL off]", lambda i: fd(trees[i % N_SETS]))
-lib.plb_set_tuning(18, 1)
-measure("fused(tree) [direct, PDL on] again", lambda i: fd(trees[i % N_SETS]))
-entries = [fz._bound[(id(t), _lib.PHASE_ALL)] for t in trees]
-execs = [e[2][1] for e in entries]
-launch = lib.plb_graph_launch
-measure("plb_graph_launch only", lambda i: launch(execs[i % N_SETS], raw_stream))
-graphs = [e[1] for e in entries]
-measure("torch CUDAGraph.replay()", lambda i: graphs[i % N_SETS].replay())
-descs = {}
-for key, (g, keep, d) in fz._graphs.items():
-    descs[d.reward] = d
-ds = [descs[t["reward"].data_ptr()] for t in trees]
-refs = [ctypes.byref(d) for d in ds]
-pipe = lib.plb_batch_pipeline_f32
-measure("plb_batch_pipeline_f32 (cached d)", lambda i: pipe(refs[i % N_SETS], _lib.PHASE_ALL, raw_stream))
-nop = lib.plb_sm_count
-measure("ctypes no-op (plb_sm_count)", lambda i: nop(), n=1000)
+for rep in range(2):
+    for mode in (0, 1):
+        lib.plb_set_tuning(21, mode)
+        measure(f"direct, PDL, reduce mode {mode}", lambda i: fd(trees[i % N_SETS]))
+        measure(f"graph, reduce mode {mode}", lambda i: fz(trees[i % N_SETS]))
+lib.plb_set_tuning(21, 0)
