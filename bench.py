@@ -481,6 +481,7 @@ def main():
     config = {"workload": workload, "T": T_STEPS, "B_per_gpu": B_ENVS, "B_total": B_ENVS * max(world, 1),
               "sharding": "env axis B split across ranks; (count,mean,M2) exchanged between all CTAs of all ranks inside the kernel when N>1",
               "l2_policy": "inputs rotate over buffer sets totalling > 2x L2, so every step reads HBM",
+              "launch": "one plb_batch_pipeline_f32 call per step on the bound descriptor; kernels launched with programmatic dependent launch",
               "timing": f"median of {args.windows} windows of {args.steps} steps (CUDA events, barrier + synchronize around each, max over ranks)"}
     cores = os.cpu_count() or 1
 

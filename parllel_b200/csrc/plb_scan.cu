@@ -316,6 +316,18 @@ scan_pipelined_kernel(const __grid_constant__ TensorMaps tm, const Params p)
     }
     if (!RESIDENT) griddep_wait();  // everything below reads or writes global memory the predecessor may own
     __syncthreads();
+    // sharded: what the last CTA's push will need from memory, fetched now by the warp that pushes (two dependent L2
+    // round trips off the tail, which every rank's normalise kernel waits for)
+    // (parked in shared memory, not in registers: the tile loop has none to spare)
+    __shared__ unsigned char *s_xch_peer[32];
+    __shared__ unsigned char *s_xch_mine;
+    __shared__ uint32_t s_xch_epoch;
+    const bool xch_preloaded = !RESIDENT && HAS_STATS && p.tail.xch.peers != nullptr && !p.tail.partials_only;
+    if (xch_preloaded && warp == 0) {
+        const XchPre pre = xch_preload(p.tail.xch);
+        s_xch_peer[lane] = pre.peer;
+        if (lane == 0) { s_xch_mine = pre.mine; s_xch_epoch = pre.epoch; }
+    }
     uint32_t tmem_warp = 0;  // this warp's lane quarter and column half of tile 0
     if (RESIDENT) {
         tmem_fence_after_sync();
@@ -709,7 +721,11 @@ scan_pipelined_kernel(const __grid_constant__ TensorMaps tm, const Params p)
     } else if (HAS_STATS && !(p.debug & 2)) {
         Sums acc;
         acc.n = (double)st_n; acc.s1 = st_s1; acc.s2 = st_s2; acc.piv = (double)st_piv;
-        moments_tail<true>(acc, p.tail, red_scratch);
+        XchPre xch_pre = xch_no_preload();
+        if (xch_preloaded && warp == 0) {  // written by this very warp
+            xch_pre.mine = s_xch_mine; xch_pre.peer = s_xch_peer[lane]; xch_pre.epoch = s_xch_epoch; xch_pre.valid = true;
+        }
+        moments_tail<true>(acc, p.tail, red_scratch, xch_pre);
     }
     if (threadIdx.x == 0) tma_store_wait<0>();
 }

@@ -298,16 +298,41 @@ __host__ __device__ __forceinline__ size_t xch_total_bytes3(int world)
     return xch_ll_offset(world) + 2 * (size_t)world * 8 * 8;
 }
 
+// What xch_push3 needs from memory, fetched by the pushing warp long before the push (at kernel start: the epoch word
+// only changes in the push itself): the pointer table entry of lane's peer, the own buffer, the current epoch.
+struct XchPre {
+    unsigned char *mine, *peer;
+    uint32_t epoch;
+    bool valid;
+};
+__device__ __forceinline__ XchPre xch_preload(const XchRef &x)
+{
+    XchPre pre;
+    const int lane = threadIdx.x & 31;
+    pre.mine = x.peers[x.rank];
+    pre.peer = lane < x.world ? x.peers[lane] : nullptr;
+    pre.epoch = *reinterpret_cast<const volatile uint32_t *>(pre.mine);
+    pre.valid = true;
+    return pre;
+}
+
 // Push this rank's sums to every rank.  Called by ONE full warp (world <= 32); lane 0 supplies them.
-__device__ __forceinline__ void xch_push3(const XchRef &x, Sums mine_sums)
+__device__ __forceinline__ XchPre xch_no_preload()
+{
+    XchPre pre;
+    pre.mine = nullptr; pre.peer = nullptr; pre.epoch = 0u; pre.valid = false;
+    return pre;
+}
+__device__ __forceinline__ void xch_push3(const XchRef &x, Sums mine_sums, const XchPre pre = xch_no_preload())
 {
     const int lane = threadIdx.x & 31;
-    unsigned char *mine = x.peers[x.rank];
-    unsigned char *peer = lane < x.world ? x.peers[lane] : nullptr;  // in flight together with the epoch round trip
+    const bool have = pre.valid;
+    unsigned char *mine = have ? pre.mine : x.peers[x.rank];
+    unsigned char *peer = have ? pre.peer : (lane < x.world ? x.peers[lane] : nullptr);  // in flight with the epoch round trip
     uint32_t epoch = 0;
     if (lane == 0) {
         uint32_t *ep = reinterpret_cast<uint32_t *>(mine);
-        epoch = *ep + 1u;
+        epoch = (have ? pre.epoch : *ep) + 1u;
         *ep = epoch;
     }
     epoch = __shfl_sync(0xffffffffu, epoch, 0);
@@ -673,7 +698,8 @@ __device__ __forceinline__ void chan_update_scalar(double b_n, double b_mean, do
 // ---------------------------------------------------------------------------------
 // WARP_PIVOT: `mine.piv` is uniform within every warp (the scans broadcast lane 0's first value).
 template <bool WARP_PIVOT = false>
-__device__ __forceinline__ void moments_tail(const Sums &mine, const MomentsTail &tail, Sums *scratch)
+__device__ __forceinline__ void moments_tail(const Sums &mine, const MomentsTail &tail, Sums *scratch,
+                                             const XchPre xch_pre = xch_no_preload())
 {
     __shared__ bool is_last;
     __syncthreads();  // scratch may have been used before
@@ -720,7 +746,7 @@ __device__ __forceinline__ void moments_tail(const Sums &mine, const MomentsTail
         if (threadIdx.x < 32) {
             if (threadIdx.x == 0) *tail.ticket = 0u;
             if (tail.dbg != nullptr && threadIdx.x == 0) tail.dbg[2] = global_timer_ns();
-            xch_push3(tail.xch, acc);  // lane 0's sums travel; the consumer writes the merged moments_out
+            xch_push3(tail.xch, acc, xch_pre);  // lane 0's sums travel; the consumer writes the merged moments_out
             if (tail.dbg != nullptr && threadIdx.x == 0) tail.dbg[3] = global_timer_ns();
         }
         return;
