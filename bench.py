@@ -57,7 +57,7 @@ def measured_peak():
 
 def measured_traffic():
     """dram__bytes_read + dram__bytes_write per launch of the dominant kernel, from the committed ncu capture."""
-    for name in ("r2_traffic.json", "r1_traffic.json"):
+    for name in ("r3_traffic.json", "r2_traffic.json", "r1_traffic.json"):
         try:
             with open(os.path.join(ROOT, "profiles", name)) as f:
                 d = json.load(f)
@@ -645,27 +645,31 @@ def main():
     # (HostBatchPipeline: H2D of batch i+1, kernels of batch i and D2H of batch i-1 overlap); every
     # step uploads its inputs and downloads its results inside the timed region
     e2e_steps = args.e2e_steps or min(args.steps, 60)
-    host_sets = [PinnedBatch(synth_batch(7000 + 10 * rank + i)) for i in range(2)]
+    # three batches in flight: with two, batch i+1 can only be submitted once batch i-1 has been downloaded, and
+    # kernels + download + host enqueue time (0.02 + 0.69 + ~0.15 ms) exceed the upload they should hide behind
+    E2E_DEPTH = 3
+    host_sets = [PinnedBatch(synth_batch(7000 + 10 * rank + i)) for i in range(E2E_DEPTH)]
     e2e_fused = FusedBatchTransforms([EstimateAdvantage(GAMMA, LAMBDA), NormalizeAdvantage(host_sets[0].tree)])
-    pipe = HostBatchPipeline(e2e_fused, device=dev)
-    for i in range(6):
-        pipe(host_sets[i % 2].tree)
+    pipe = HostBatchPipeline(e2e_fused, device=dev, n_slots=E2E_DEPTH)
+    for i in range(3 * E2E_DEPTH):
+        pipe(host_sets[i % E2E_DEPTH].tree)
     torch.cuda.synchronize()
     lat = []
     for i in range(10):  # one isolated batch at a time: upload, kernels, download, wait
         t0 = time.perf_counter()
-        pipe(host_sets[i % 2].tree)
+        pipe(host_sets[i % E2E_DEPTH].tree)
         lat.append(time.perf_counter() - t0)
     if distributed:
         dist.barrier()
     t0 = time.perf_counter()
-    prev = None
+    handles = []
     for i in range(e2e_steps):
-        h = pipe.submit(host_sets[i % 2].tree)
-        if prev is not None:
-            prev.wait()  # batch i-1 is complete in host memory before its buffers are reused
-        prev = h
-    prev.wait()
+        handles.append(pipe.submit(host_sets[i % E2E_DEPTH].tree))
+        if i >= E2E_DEPTH - 1:
+            # batch i-2 is complete in host memory before its buffers are reused (by batch i+1)
+            handles[i - (E2E_DEPTH - 1)].wait()
+    for h in handles[-(E2E_DEPTH - 1):]:
+        h.wait()
     torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - t0) * 1e3  # host wall clock: results are in host memory at this point
     if distributed:
@@ -718,9 +722,9 @@ def main():
                 "single_batch_latency_ms": statistics.median(lat) * 1e3,
                 "per_rank_h2d_GBs": h2d / (e2e_ms / e2e_steps * 1e-3) / 1e9, "per_rank_d2h_GBs": d2h / (e2e_ms / e2e_steps * 1e-3) / 1e9,
                 "cpus_bound_per_rank": numa_cpus,
-                "note": "value is PIPELINED throughput (batch i+1 uploads while i computes and i-1 downloads); an RL iteration "
+                "note": "value is PIPELINED throughput (batch i+1 uploads while i computes and i-1 / i-2 download); an RL iteration "
                         "that holds one batch sees single_batch_latency_ms",
-                "api": "HostBatchPipeline(FusedBatchTransforms([EstimateAdvantage, NormalizeAdvantage])).submit(tree)/wait() on pinned numpy trees, 2 slots"},
+                "api": "HostBatchPipeline(FusedBatchTransforms([EstimateAdvantage, NormalizeAdvantage]), n_slots=3).submit(tree)/wait() on pinned numpy trees, three batches in flight"},
         "gpu_launches": args.steps * kernels_per_step,
         "kernels_per_step": kernels_per_step,
         "kernels_per_step_source": "plb_launch_counters() around one step (every timed step is one plb_batch_pipeline_f32 call on the cached descriptor; its kernels are launched with programmatic dependent launch)",

@@ -81,12 +81,13 @@ class PinnedBatch:
 
 
 class _Handle:
-    def __init__(self, event: torch.cuda.Event, tree) -> None:
-        self._event, self.tree = event, tree
+    def __init__(self, events, tree) -> None:
+        self._events, self.tree = events, tree
 
     def wait(self):
         """Block until this batch's results are in the caller's host buffers; returns the tree."""
-        self._event.synchronize()
+        for ev in self._events:
+            ev.synchronize()
         return self.tree
 
 
@@ -108,22 +109,34 @@ class HostBatchPipeline:
         self.device = torch.device(device) if device is not None else default_device()
         self.n_slots = n_slots
         self._slots: list = []
+        self._views: dict = {}
         self._slot_free: list = []
         self._next = 0
-        self._h2d = torch.cuda.Stream(self.device)
+        # two streams per direction: consecutive copies on ONE stream leave the link idle between transfers (each
+        # waits for its predecessor's completion before its DMA is set up: ~25 us per leaf, 10 % of a C1 step);
+        # leaves alternate between the two, so one transfer's set-up hides behind the other's payload
+        self._h2d = [torch.cuda.Stream(self.device) for _ in range(2)]
         self._compute = torch.cuda.Stream(self.device)
-        self._d2h = torch.cuda.Stream(self.device)
+        self._d2h = [torch.cuda.Stream(self.device) for _ in range(2)]
         self._outputs = list(_OUTPUTS_ALWAYS)
         if fused.norm_rewards is not None:
             self._outputs += ["reward", "past_return"]
         elif fused.clip is not None:
             self._outputs += ["reward"]
 
-    @staticmethod
-    def _host_view(leaf) -> torch.Tensor:
+    def _host_view(self, leaf) -> torch.Tensor:
+        """Torch view of a host leaf, page-locked in place; remembered per leaf object (the samplers hand the same
+        buffers over every iteration), so a submit costs no pointer-attribute queries."""
+        hit = self._views.get(id(leaf))
+        if hit is not None and hit[0] is leaf:
+            return hit[1]
         arr = leaf.detach().numpy() if isinstance(leaf, torch.Tensor) else np.asarray(leaf)
         pin_in_place(arr)
-        return torch.from_numpy(arr)
+        view = torch.from_numpy(arr)
+        if len(self._views) > 256:
+            self._views.clear()
+        self._views[id(leaf)] = (leaf, view)  # holding the leaf keeps its id from being reused
+        return view
 
     def _make_slot(self, tree) -> ArrayDict:
         def dev_like(leaf):
@@ -142,27 +155,36 @@ class HostBatchPipeline:
             self._slots.append(self._make_slot(tree))
             self._slot_free.append(None)
         slot = self._slots[k]
-        with torch.cuda.stream(self._h2d):
-            if self._slot_free[k] is not None:
-                self._h2d.wait_event(self._slot_free[k])  # previous user of the slot has been downloaded
-            for n in _INPUTS:
-                if n in tree:
-                    slot[n].copy_(self._host_view(tree[n]), non_blocking=True)
-            slot["agent_info"]["value"].copy_(self._host_view(tree["agent_info"]["value"]), non_blocking=True)
-            uploaded = torch.cuda.Event()
-            uploaded.record(self._h2d)
+        uploads = [(slot[n], self._host_view(tree[n])) for n in _INPUTS if n in tree]
+        uploads.append((slot["agent_info"]["value"], self._host_view(tree["agent_info"]["value"])))
+        uploads.sort(key=lambda pair: -pair[1].numel() * pair[1].element_size())  # big leaves first, one per stream
+        uploaded = []
+        for j, stream in enumerate(self._h2d):
+            with torch.cuda.stream(stream):
+                if self._slot_free[k] is not None:
+                    for ev in self._slot_free[k]:
+                        stream.wait_event(ev)  # previous user of the slot has been downloaded
+                for dst, src in uploads[j::len(self._h2d)]:
+                    dst.copy_(src, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(stream)
+                uploaded.append(ev)
         with torch.cuda.stream(self._compute):
-            self._compute.wait_event(uploaded)
+            for ev in uploaded:
+                self._compute.wait_event(ev)
             self.fused(slot)
             computed = torch.cuda.Event()
             computed.record(self._compute)
-        with torch.cuda.stream(self._d2h):
-            self._d2h.wait_event(computed)
-            for n in self._outputs:
-                if n in tree:
-                    self._host_view(tree[n]).copy_(slot[n], non_blocking=True)
-            done = torch.cuda.Event()
-            done.record(self._d2h)
+        downloads = [(self._host_view(tree[n]), slot[n]) for n in self._outputs if n in tree]
+        done = []
+        for j, stream in enumerate(self._d2h):
+            with torch.cuda.stream(stream):
+                stream.wait_event(computed)
+                for dst, src in downloads[j::len(self._d2h)]:
+                    dst.copy_(src, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(stream)
+                done.append(ev)
         self._slot_free[k] = done
         return _Handle(done, tree)
 
