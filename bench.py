@@ -519,7 +519,7 @@ def main():
     from parllel_b200.transforms import EstimateAdvantage, FusedBatchTransforms, NormalizeAdvantage
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device"
-    numa_cpus = bind_to_gpu_numa(local_rank) if world > 1 else None
+    numa_cpus = None  # bound right before the host-buffer (e2e) leg: see below
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     distributed = world > 1
@@ -554,7 +554,9 @@ def main():
     torch.cuda.synchronize()
     _debug("warm-up done")
 
-    with ClockSampler(local_rank) as clocks:
+    # clocks of the GPU whose rank prints the line; the other ranks do not poll NVML (every rank is coupled to every
+    # other one through the statistics exchange, so a hiccup on any GPU is paid by all of them)
+    with ClockSampler(local_rank, period_s=0.05 if rank == 0 else 3600.0) as clocks:
         windows_ms = timed_windows(step, args.steps, max(args.windows, 1), dev, dist, distributed)
         _debug("timed windows done")
 
@@ -645,6 +647,10 @@ def main():
     # (HostBatchPipeline: H2D of batch i+1, kernels of batch i and D2H of batch i-1 overlap); every
     # step uploads its inputs and downloads its results inside the timed region
     e2e_steps = args.e2e_steps or min(args.steps, 60)
+    if world > 1:
+        # host threads and pinned staging memory on the GPU's own socket (the device-resident legs above ran unbound,
+        # like any launcher-started process)
+        numa_cpus = bind_to_gpu_numa(local_rank)
     # three batches in flight: with two, batch i+1 can only be submitted once batch i-1 has been downloaded, and
     # kernels + download + host enqueue time (0.02 + 0.69 + ~0.15 ms) exceed the upload they should hide behind
     E2E_DEPTH = 3
