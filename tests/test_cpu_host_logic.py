@@ -176,3 +176,22 @@ def test_transform_constructor_contracts_cpu():
     assert tf.only_valid and float(tf.return_statistics.count) == 2.0 and float(tf.return_statistics.var) == 1.0
     ea = EstimateAdvantage(0.99, 1.0)
     assert ea.discount == 0.99 and ea.gae_lambda == 1.0
+
+
+def test_fused_batch_transforms_launch_modes_and_tuning_keys():
+    """The launch path is a constructor choice ("direct": bound descriptor + programmatic dependent launch, the
+    default; "graph": CUDA-graph replay; use_cuda_graph=False: rebuilt every call); the experiment switches that
+    select kernel variants are plain host state and must be settable without a GPU."""
+    from parllel_b200 import _lib
+    from parllel_b200.transforms import EstimateAdvantage, FusedBatchTransforms
+    assert FusedBatchTransforms([EstimateAdvantage(0.99, 0.95)]).launch in ("direct", "graph")
+    assert FusedBatchTransforms([EstimateAdvantage(0.99, 0.95)], launch="graph").launch == "graph"
+    assert FusedBatchTransforms([EstimateAdvantage(0.99, 0.95)], launch="direct").launch == "direct"
+    assert FusedBatchTransforms([EstimateAdvantage(0.99, 0.95)], use_cuda_graph=False).launch == "eager"
+    with pytest.raises(ValueError):
+        FusedBatchTransforms([EstimateAdvantage(0.99, 0.95)], launch="bogus")
+    lib = _lib.load()
+    for key, value in ((18, 1), (20, 1024), (21, 0), (17, 0)):
+        assert lib.plb_set_tuning(key, value) == 0
+    assert lib.plb_set_tuning(9999, 0) != 0
+    assert b"unknown tuning key" in lib.plb_last_error()
