@@ -180,6 +180,13 @@ class FusedBatchTransforms(Transform):
         st = Staging(nr.return_statistics.device if nr is not None else None)
         d = _lib.BatchPipeline()
         keep = []  # tensors that must outlive the launch
+        snapshots = []  # True where a row vector had to be COPIED to make it dense: such a call must not be bound or
+        #                 captured (a replay would read the copy, not what the tree holds by then)
+
+        def flat(t: torch.Tensor) -> torch.Tensor:
+            f = t.reshape(-1).contiguous()
+            snapshots.append(f.data_ptr() != t.data_ptr())
+            return f
 
         reward_leaf = sample_tree["reward"] if (nr or self.clip or est) else None
         reward = st.view(reward_leaf, writeback=bool(nr or self.clip)) if reward_leaf is not None else None
@@ -213,7 +220,7 @@ class FusedBatchTransforms(Transform):
                 if nr._carry_done is None:
                     nr._carry_done = torch.zeros(B, dtype=torch.bool, device=st.device)
                 prev_done = nr._carry_done
-            prev_ret, prev_done = prev_ret.reshape(-1).contiguous(), prev_done.reshape(-1).contiguous()
+            prev_ret, prev_done = flat(prev_ret), flat(prev_done)
             keep += [prev_ret, prev_done]
             d.previous_return, d.previous_done = prev_ret.data_ptr(), prev_done.data_ptr()
             if nr._carry_return is not None and nr._carry_done is not None:
@@ -231,7 +238,7 @@ class FusedBatchTransforms(Transform):
             d.clip_hi = _lib.NAN if self.clip.reward_max is None else float(self.clip.reward_max)
         if est is not None:
             value = st.view(sample_tree["agent_info"]["value"])
-            boot = st.view(sample_tree["bootstrap_value"]).reshape(-1).contiguous()
+            boot = flat(st.view(sample_tree["bootstrap_value"]))
             adv = st.view(sample_tree["advantage"], writeback=True)
             ret = st.view(sample_tree["return_"], writeback=True)
             if value.dim() != 2:
@@ -310,8 +317,9 @@ class FusedBatchTransforms(Transform):
                     nr._carry_done.copy_(done[T - 1])
 
         # the NCCL all-gathers of the sharded chain are captured into the graph as well
-        graphable = self.use_cuda_graph and not st.staged and not capturing
-        if self.launch == "direct" and self.use_cuda_graph and not st.staged and not split_phases and not carry_copies:
+        graphable = self.use_cuda_graph and not st.staged and not capturing and not any(snapshots)
+        if self.launch == "direct" and self.use_cuda_graph and not st.staged and not split_phases and not carry_copies \
+                and not any(snapshots):
             enqueue()
             self._bind_direct(sample_tree, phases, d, keep, dev)
         elif not graphable:

@@ -595,3 +595,28 @@ def test_c2_full_size_observation_step_properties():
         results[variant] = d
     assert (results[1] - results[2]).abs().max().item() <= 2e-6
     assert (results[1] - results[4]).abs().max().item() <= 2e-6
+
+
+@pytest.mark.parametrize("launch", ["graph", "direct"])
+def test_strided_bootstrap_value_is_read_afresh_on_every_call(launch):
+    """A row vector that has to be COPIED to become dense (here: every second element of a wider buffer) must not be
+    frozen into a bound descriptor or a captured graph: every call reads what the tree holds at that moment."""
+    from parllel_b200 import ArrayDict
+    from parllel_b200.transforms import EstimateAdvantage, FusedBatchTransforms, NormalizeAdvantage
+    T, B = 64, 128
+    rng = np.random.default_rng(21)
+    batch = make_batch(rng, T, B, 0.02)
+    wide = torch.zeros(2 * B, device="cuda")
+    tree = ArrayDict({"reward": torch.from_numpy(batch["reward"]).cuda(), "done": torch.from_numpy(batch["done"]).cuda(),
+                      "agent_info": {"value": torch.from_numpy(batch["value"]).cuda()}, "bootstrap_value": wide[::2],
+                      "advantage": torch.empty(T, B, device="cuda"), "return_": torch.empty(T, B, device="cuda")})
+    fused = FusedBatchTransforms([EstimateAdvantage(0.99, 0.95), NormalizeAdvantage(tree)], launch=launch)
+    for it in range(4):
+        boot = rng.standard_normal(B).astype(np.float32)
+        wide[::2] = torch.from_numpy(boot).cuda()
+        fused(tree)
+        adv, ret = np.empty_like(batch["value"]), np.empty_like(batch["value"])
+        O.compute_gae_advantage(batch["reward"], batch["value"], batch["done"], boot, 0.99, 0.95, adv, ret)
+        O.normalize_advantage(adv)
+        assert_within_tolerance(tree["return_"].cpu().numpy(), ret, what=f"call {it} return_")
+        assert_within_tolerance(tree["advantage"].cpu().numpy(), adv, what=f"call {it} advantage")
