@@ -620,3 +620,26 @@ def test_strided_bootstrap_value_is_read_afresh_on_every_call(launch):
         O.normalize_advantage(adv)
         assert_within_tolerance(tree["return_"].cpu().numpy(), ret, what=f"call {it} return_")
         assert_within_tolerance(tree["advantage"].cpu().numpy(), adv, what=f"call {it} advantage")
+
+
+def test_running_mean_std_model_checkpoint_round_trip(golden):
+    """restoring a checkpoint must restore the statistics the NEXT update merges into.  A model that is
+    saved after two updates and restored into a fresh instance must continue exactly like the original -- and like
+    the reference's third update (golden `rms2_*`)."""
+    from parllel_b200.models import RunningMeanStdModel
+    g = golden("metrics")
+    a = RunningMeanStdModel((5, 3))
+    for k in range(2):
+        a.update(torch.from_numpy(g["rms_x"][k]).cuda())
+    saved = {k: v.clone() for k, v in a.state_dict().items()}
+    b = RunningMeanStdModel((5, 3))
+    b.load_state_dict(saved)
+    np.testing.assert_array_equal(b.mean.cpu().numpy(), a.mean.cpu().numpy())
+    for m in (a, b):
+        m.update(torch.from_numpy(g["rms_x"][2]).cuda())
+    assert float(b.count) == float(a.count) == float(g["rms2_count"])
+    # the restored working statistics come from the float32 buffers, the original's are float64: equal to float32 rounding
+    np.testing.assert_allclose(b.mean.cpu().numpy(), a.mean.cpu().numpy(), rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(b.var.cpu().numpy(), a.var.cpu().numpy(), rtol=1e-6)
+    np.testing.assert_allclose(b.mean.cpu().numpy(), g["rms2_mean"], rtol=2e-6, atol=1e-7)
+    np.testing.assert_allclose(b.var.cpu().numpy(), g["rms2_var"], rtol=1e-5)
