@@ -10,8 +10,10 @@ and runs it as ONE C call (``plb_batch_pipeline_f32``, csrc/plb_pipeline.cu): th
 rescale/clip rides on the advantage scan's load path and the advantage moments on its store path,
 so the batch is streamed 3 times instead of 6.  Results are those of calling the transforms one
 after the other; the wrapped transform objects keep owning their state (``return_statistics``).
-On device-resident trees the launch sequence is captured into a CUDA graph per set of leaf
-addresses and replayed, which removes the host launch cost from the sampler loop.
+On device-resident trees the filled descriptor is bound to the tree object, so that a sampler-loop
+call is one ctypes call whose kernels are launched with programmatic dependent launch
+(``launch="direct"``, default), or the launch sequence is captured into a CUDA graph per set of leaf
+addresses and replayed (``launch="graph"``).
 
 Pass ``[FusedBatchTransforms(batch_transforms)]`` to the sampler instead of ``batch_transforms``.
 """
@@ -154,9 +156,10 @@ class FusedBatchTransforms(Transform):
         return True
 
     def __call__(self, sample_tree, phases: int = _lib.PHASE_ALL):
-        # fast path: a graph was captured for exactly these leaves -> replay it (a few microseconds of host time,
-        # which matters: the sharded step re-synchronises all ranks every ~30 us, so the slowest host paces them);
-        # inside somebody else's stream capture the launches are enqueued as they are (no nested graphs)
+        # fast path: this tree object is bound, with exactly these leaves at exactly these addresses, either to a filled
+        # descriptor (one C call launches the kernels -- also inside somebody else's stream capture) or to a captured
+        # graph (replayed, unless a capture is going on: no nested graphs).  A few microseconds of host time, which
+        # matters: the sharded step re-synchronises all ranks every ~25 us, so the slowest host paces them
         if self._bound:
             entry = self._bound.get((id(sample_tree), phases))
             if entry is not None and self._still_bound(sample_tree, entry[0]):
