@@ -5,6 +5,10 @@
 
 Both run through the C ABI (``plb_batch_moments_f32`` / ``plb_residual_moments_f32`` /
 ``plb_valid_prefix_u8``); there is no CPU path.
+
+* ``valid_mean``          -- parllel/torch/utils.py:42-62.  The one exception: the learners call it on loss terms, so
+  it has to stay inside autograd; it is a handful of torch reductions on whatever device the loss lives on, kept here
+  so that code which imports it from parllel's utilities finds it next to ``explained_variance``.
 """
 from __future__ import annotations
 
@@ -64,3 +68,22 @@ def valid_mask(done: torch.Tensor, out: torch.Tensor | None = None) -> torch.Ten
     _lib.check(_lib.load().plb_valid_prefix_u8(dptr, dld, T, B, optr, old, stream_ptr(done.device)),
                "plb_valid_prefix_u8")
     return out
+
+
+def valid_mean(tensor: torch.Tensor, valid: torch.Tensor | None = None, dim=None) -> torch.Tensor:
+    """Masked mean of a loss term, differentiable (parllel/torch/utils.py:42-62, same three cases):
+
+    * no mask: the plain mean (over ``dim`` if given, else over everything);
+    * mask, no ``dim``: the mean of the selected elements; a ``[T, B]`` mask selects whole trailing slices of a
+      ``[T, B, ...]`` tensor;
+    * mask and ``dim``: the mask is extended over the trailing axes, masked-out entries count as zero, and the sum
+      along ``dim`` is divided by the number of NON-ZERO entries left -- the reference counts with
+      ``count_nonzero`` on the masked values, so a valid element that happens to be exactly 0 is not counted; kept.
+    """
+    if valid is None:
+        return tensor.mean(dim=() if dim is None else dim)
+    if dim is None:
+        return tensor[valid].mean()
+    mask = valid.reshape(valid.shape + (1,) * (tensor.ndim - valid.ndim))
+    kept = torch.where(mask, tensor, torch.zeros((), dtype=tensor.dtype, device=tensor.device))
+    return kept.sum(dim=dim) / kept.count_nonzero(dim=dim)

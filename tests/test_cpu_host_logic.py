@@ -195,3 +195,32 @@ def test_fused_batch_transforms_launch_modes_and_tuning_keys():
         assert lib.plb_set_tuning(key, value) == 0
     assert lib.plb_set_tuning(9999, 0) != 0
     assert b"unknown tuning key" in lib.plb_last_error()
+
+
+def test_valid_mean_matches_the_reference_including_autograd():
+    """parllel/torch/utils.py:42-62 -- all three call forms, values and gradients."""
+    from parllel_b200.metrics import valid_mean
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(6, 5, 4, generator=g)
+    x[1, 2, 0] = 0.0  # a valid element that is exactly zero: the reference's count_nonzero does not count it
+    valid = torch.rand(6, 5, generator=g) < 0.7
+    valid[1, 2] = True
+    cases = [dict(), dict(dim=(0, 1)), dict(valid=valid), dict(valid=valid, dim=(0, 1)), dict(valid=valid, dim=0)]
+    # independent expectations
+    assert torch.allclose(valid_mean(x), x.mean())
+    assert torch.allclose(valid_mean(x, valid), x[valid].mean())
+    m = valid[..., None].expand_as(x)
+    expect = (x * m).sum(dim=(0, 1)) / ((x * m) != 0).sum(dim=(0, 1))
+    assert torch.allclose(valid_mean(x, valid, dim=(0, 1)), expect)
+    if not reference_available():
+        return
+    load_reference()
+    from parllel.torch.utils import valid_mean as ref_valid_mean
+    for kw in cases:
+        a = x.clone().requires_grad_(True)
+        b = x.clone().requires_grad_(True)
+        got, ref = valid_mean(a, **kw), ref_valid_mean(b, **kw)
+        assert torch.equal(got, ref), kw
+        got.sum().backward()
+        ref.sum().backward()
+        assert torch.equal(a.grad, b.grad), kw
