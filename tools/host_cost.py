@@ -49,9 +49,18 @@ def measure(name, call, n=3000):
           f"p50 {np.percentile(per, 50):6.2f}  p90 {np.percentile(per, 90):6.2f}  p99 {np.percentile(per, 99):6.2f}  max {per.max():8.2f} us", flush=True)
 
 
-for rep in range(2):
-    for mode in (0, 1):
-        lib.plb_set_tuning(21, mode)
-        measure(f"direct, PDL, reduce mode {mode}", lambda i: fd(trees[i % N_SETS]))
-        measure(f"graph, reduce mode {mode}", lambda i: fz(trees[i % N_SETS]))
+measure("fused(tree) [graph replay]", lambda i: fz(trees[i % N_SETS]))
+measure("fused(tree) [direct, PDL on]", lambda i: fd(trees[i % N_SETS]))
+lib.plb_set_tuning(18, 0)
+measure("fused(tree) [direct, PDL off]", lambda i: fd(trees[i % N_SETS]))
+lib.plb_set_tuning(18, 1)
+# A/B inside one process (boxes of the pool differ by ~1 us per step): the normalise kernel's prologue
+lib.plb_set_tuning(21, 1)
+measure("direct, PDL on, serial partial loads (key 21 = 1)", lambda i: fd(trees[i % N_SETS]))
 lib.plb_set_tuning(21, 0)
+measure("direct, PDL on, one-round-trip prologue", lambda i: fd(trees[i % N_SETS]))
+launch = lib.plb_graph_launch
+execs = [fz._bound[(id(t), _lib.PHASE_ALL)][2][1] for t in trees]
+measure("plb_graph_launch only", lambda i: launch(execs[i % N_SETS], raw_stream))
+nop = lib.plb_sm_count
+measure("ctypes no-op (plb_sm_count)", lambda i: nop(), n=1000)
