@@ -90,7 +90,7 @@ PLB_API int plb_sm_count(void);
  *           one record of partial sums per rank (default), 1 resident kernel
  *   key 18: programmatic dependent launch of the streaming kernels (scans, advantage normalise, index generation):
  *           1 (default) on, 0 off -- the kernels then start only when their predecessor on the stream has retired
- *   key 20: CTA size of the sharded advantage-normalise kernel: 256, 512 or 1024 (default) threads, one CTA per SM at 1024
+ *   key 20: CTA size of the sharded advantage-normalise kernel: 256 (default), 512 or 1024 threads (one CTA per SM at 1024)
  *   key 21: experiments: 1 = the normalise prologue reads the scan's partial sums one after the other (round-2 code)
  *   key 16: 1 = replay gather through the load/store-unit path only (default 0: TMA-staged rows of >= 128 B)
  *   key 13: 0 = index generation always by the single-CTA kernel (default 1: 8-CTA cluster kernel)

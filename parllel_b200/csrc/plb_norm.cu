@@ -64,8 +64,11 @@ static int g_normadv_ctas_per_sm = 4;
 void set_normadv_ctas_per_sm(int v) { g_normadv_ctas_per_sm = v > 0 ? v : 4; }
 static int g_normadv_reduce_mode = 0;     // experiments: 1 = serial partial loads in the normalise prologue (key 21)
 void set_normadv_reduce_mode(int v) { g_normadv_reduce_mode = v; }
-static int g_normadv_xch_threads = 1024;  // CTA size of the sharded normalise kernel (plb_set_tuning key 20)
-void set_normadv_xch_threads(int v) { g_normadv_xch_threads = (v == 256 || v == 512 || v == 1024) ? v : 1024; }
+// CTA size of the sharded normalise kernel (plb_set_tuning key 20).  256 is the configuration of the best 8-GPU
+// measurement (26.8 us per step); 512 / 1024 (fewer polling warps per SM) measured the same at two GPUs and were
+// not measured in isolation at eight.
+static int g_normadv_xch_threads = 256;
+void set_normadv_xch_threads(int v) { g_normadv_xch_threads = (v == 256 || v == 512 || v == 1024) ? v : 256; }
 
 template <class F>
 static int launch_elementwise(float *x, int64_t ld_x, int64_t rows, int64_t cols, bool col_dependent, F f,
@@ -210,8 +213,7 @@ normalize_advantage_partials_kernel(float *__restrict__ x, int64_t ld_x, int64_t
 
 // Multi-GPU variant: the producer's tail pushed this rank's moments to every peer; each CTA waits
 // for all ranks' flags and merges in rank order in its prologue (warp 0), the first loads in flight.
-// CTAs of up to 1024 threads, one per SM: every CTA's first warp reads the same few record lines, and with four
-// 256-thread CTAs per SM those reads alone serialised in L2 for ~3 us at eight ranks (plb_set_tuning key 20).
+// (CTAs of up to 1024 threads can be selected with plb_set_tuning key 20: a quarter of the polling warps.)
 __global__ void __launch_bounds__(1024)
 normalize_advantage_xch_kernel(float *__restrict__ x, int64_t ld_x, int64_t rows, int64_t cols, const XchRef xch,
                                float eps, double *__restrict__ moments_out, unsigned long long *dbg)

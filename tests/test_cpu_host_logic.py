@@ -191,7 +191,7 @@ def test_fused_batch_transforms_launch_modes_and_tuning_keys():
     with pytest.raises(ValueError):
         FusedBatchTransforms([EstimateAdvantage(0.99, 0.95)], launch="bogus")
     lib = _lib.load()
-    for key, value in ((18, 1), (20, 1024), (21, 0), (17, 0)):
+    for key, value in ((18, 1), (20, 256), (21, 0), (17, 0)):
         assert lib.plb_set_tuning(key, value) == 0
     assert lib.plb_set_tuning(9999, 0) != 0
     assert b"unknown tuning key" in lib.plb_last_error()

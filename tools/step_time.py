@@ -58,7 +58,7 @@ for name in (sys.argv[1:] or ["c1", "c4"]):
         if rank == 0:
             print(f"world {world} {name} [T={T}, B={B}/rank] route {route} launch {launch} xch threads {threads}: {us:.2f} us/step", flush=True)
         del fz
-    lib.plb_set_tuning(20, 1024)
+    lib.plb_set_tuning(20, 256)
     del trees
 lib.plb_set_tuning(17, 0)
 if world > 1:
